@@ -1,0 +1,245 @@
+// Fused softmax(QK^T*scale + mask) V for bf16, head dims 32/64/128: online-softmax tiles of 64 queries x 64 keys,
+// cp.async double-buffered K/V, ldmatrix + mma.sync.m16n8k16 (fp32 accumulate), causal / per-batch key-length masks.
+// Serves: LLaMA prefill + decode (modeling_llama.py:199-289 semantics), DINOv2 global attention
+// (modeling_dinov2.py:153-179) and the DDETR decoder self-attention (modeling_deformable_detr.py:453-516).
+#include "ptx.cuh"
+#include "capi_common.h"
+
+namespace gb {
+
+struct AttnParams {
+    const __nv_bfloat16* q; long long q_bs, q_rs;   // q[b*q_bs + i*q_rs + h*D + d]
+    const __nv_bfloat16* k; long long k_bs, k_hs, k_rs;  // k[b*k_bs + h*k_hs + j*k_rs + d]
+    const __nv_bfloat16* v; long long v_bs, v_hs, v_rs;
+    __nv_bfloat16* o; long long o_bs, o_rs;          // o[b*o_bs + i*o_rs + h*D + d]
+    const int* kv_len;                               // optional [B]: keys >= kv_len[b] are masked
+    int Sq, Sk, H;
+    int q_pos0;      // causal: key j visible to query i iff j <= q_pos0 + i
+    float scale_log2;  // softmax scale * log2(e)
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int ATT_BM = 64, ATT_BN = 64, ATT_THREADS = 128;
+
+template <int D, bool CAUSAL>
+__global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnParams p) {
+    constexpr int LDS = D + 8;           // padded smem row (elements)
+    constexpr int CHUNKS = D / 8;        // 16-byte chunks per row
+    extern __shared__ __align__(16) uint8_t smem_att[];
+    __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_att);
+    __nv_bfloat16* Ks = Qs + ATT_BM * LDS;       // [2][BN][LDS]
+    __nv_bfloat16* Vs = Ks + 2 * ATT_BN * LDS;   // [2][BN][LDS]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int q0 = qt * ATT_BM;
+    int sk = p.Sk;
+    if (p.kv_len) sk = min(sk, p.kv_len[b]);
+    int k_end = sk;
+    if (CAUSAL) k_end = min(sk, p.q_pos0 + min(q0 + ATT_BM, p.Sq));
+    const int n_blocks = (k_end + ATT_BN - 1) / ATT_BN;
+
+    const __nv_bfloat16* qg = p.q + (long long)b * p.q_bs + (long long)h * D;
+    const __nv_bfloat16* kg = p.k + (long long)b * p.k_bs + (long long)h * p.k_hs;
+    const __nv_bfloat16* vg = p.v + (long long)b * p.v_bs + (long long)h * p.v_hs;
+
+    // ---- async load of Q tile and first K/V block
+    for (int c = tid; c < ATT_BM * CHUNKS; c += ATT_THREADS) {
+        const int r = c / CHUNKS, ch = c % CHUNKS;
+        const bool ok = q0 + r < p.Sq;
+        cp_async16(Qs + r * LDS + ch * 8, qg + (long long)(ok ? q0 + r : 0) * p.q_rs + ch * 8, ok);
+    }
+    auto load_kv = [&](int blk, int buf) {
+        const int j0 = blk * ATT_BN;
+        for (int c = tid; c < ATT_BN * CHUNKS; c += ATT_THREADS) {
+            const int r = c / CHUNKS, ch = c % CHUNKS;
+            const bool ok = j0 + r < sk;
+            const long long row = ok ? j0 + r : 0;
+            cp_async16(Ks + (buf * ATT_BN + r) * LDS + ch * 8, kg + row * p.k_rs + ch * 8, ok);
+            cp_async16(Vs + (buf * ATT_BN + r) * LDS + ch * 8, vg + row * p.v_rs + ch * 8, ok);
+        }
+    };
+    if (n_blocks > 0) load_kv(0, 0);
+    cp_async_commit();
+
+    float acc_o[D / 8][4];
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) { acc_o[i][0] = acc_o[i][1] = acc_o[i][2] = acc_o[i][3] = 0.f; }
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    uint32_t qf[D / 16][4];
+
+    const int row_in_warp0 = lane >> 2;              // accumulator rows: row_in_warp0 and +8
+    const int qrow0 = q0 + warp * 16 + row_in_warp0;  // global query index of c0/c1 ; +8 for c2/c3
+
+    for (int blk = 0; blk < n_blocks; ++blk) {
+        const int buf = blk & 1;
+        if (blk + 1 < n_blocks) load_kv(blk + 1, buf ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        if (blk == 0) {
+#pragma unroll
+            for (int ks = 0; ks < D / 16; ++ks) {
+                const uint32_t addr = smem_u32(Qs + (warp * 16 + (lane & 15)) * LDS + ks * 16 + (lane >> 4) * 8);
+                ldsm_x4(addr, qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+            }
+        }
+        // ---- S = Q K^T  (16 x 64 per warp)
+        float s[ATT_BN / 8][4];
+#pragma unroll
+        for (int i = 0; i < ATT_BN / 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+        const __nv_bfloat16* kb = Ks + buf * ATT_BN * LDS;
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) {
+#pragma unroll
+            for (int np = 0; np < ATT_BN / 16; ++np) {
+                uint32_t b0, b1, b2, b3;
+                const int n = np * 16 + (lane >> 4) * 8 + (lane & 7);
+                const int kk = ks * 16 + ((lane >> 3) & 1) * 8;
+                ldsm_x4(smem_u32(kb + n * LDS + kk), b0, b1, b2, b3);
+                mma_bf16_16816(s[2 * np], qf[ks], b0, b1);
+                mma_bf16_16816(s[2 * np + 1], qf[ks], b2, b3);
+            }
+        }
+        // ---- mask + online softmax
+        const int j_base = blk * ATT_BN + (lane & 3) * 2;
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int nt = 0; nt < ATT_BN / 8; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = j_base + nt * 8 + (e & 1);
+                const int qi = qrow0 + (e >> 1) * 8;
+                bool ok = j < sk;
+                if (CAUSAL) ok = ok && (j <= p.q_pos0 + qi);
+                const float x = ok ? s[nt][e] * p.scale_log2 : -INFINITY;
+                s[nt][e] = x;
+                mx[e >> 1] = fmaxf(mx[e >> 1], x);
+            }
+        }
+        float corr[2], m_safe[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+            const float m_new = fmaxf(m_run[r], mx[r]);
+            m_safe[r] = (m_new == -INFINITY) ? 0.f : m_new;
+            corr[r] = exp2f(m_run[r] - m_safe[r]);  // m_run = -inf -> 0
+            m_run[r] = m_new;
+        }
+        float rs[2] = {0.f, 0.f};
+        uint32_t pf[ATT_BN / 16][4];
+#pragma unroll
+        for (int nt = 0; nt < ATT_BN / 8; ++nt) {
+            const float p0 = exp2f(s[nt][0] - m_safe[0]);
+            const float p1 = exp2f(s[nt][1] - m_safe[0]);
+            const float p2 = exp2f(s[nt][2] - m_safe[1]);
+            const float p3 = exp2f(s[nt][3] - m_safe[1]);
+            rs[0] += p0 + p1;
+            rs[1] += p2 + p3;
+            pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+            pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) l_run[r] = l_run[r] * corr[r] + rs[r];
+#pragma unroll
+        for (int dt = 0; dt < D / 8; ++dt) {
+            acc_o[dt][0] *= corr[0]; acc_o[dt][1] *= corr[0];
+            acc_o[dt][2] *= corr[1]; acc_o[dt][3] *= corr[1];
+        }
+        // ---- O += P V
+        const __nv_bfloat16* vb = Vs + buf * ATT_BN * LDS;
+#pragma unroll
+        for (int kt = 0; kt < ATT_BN / 16; ++kt) {
+#pragma unroll
+            for (int dp = 0; dp < D / 16; ++dp) {
+                uint32_t b0, b1, b2, b3;
+                const int kr = kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int dc = dp * 16 + (lane >> 4) * 8;
+                ldsm_x4_t(smem_u32(vb + kr * LDS + dc), b0, b1, b2, b3);
+                mma_bf16_16816(acc_o[2 * dp], pf[kt], b0, b1);
+                mma_bf16_16816(acc_o[2 * dp + 1], pf[kt], b2, b3);
+            }
+        }
+        __syncthreads();  // everyone done with buf before it is refilled two iterations later
+    }
+    cp_async_wait<0>();
+
+    // ---- finalize: O /= l
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+    }
+    const float inv0 = l_run[0] > 0.f ? 1.f / l_run[0] : 0.f;
+    const float inv1 = l_run[1] > 0.f ? 1.f / l_run[1] : 0.f;
+    __nv_bfloat16* og = p.o + (long long)b * p.o_bs + (long long)h * D;
+#pragma unroll
+    for (int dt = 0; dt < D / 8; ++dt) {
+        const int d = dt * 8 + (lane & 3) * 2;
+        if (qrow0 < p.Sq)
+            *reinterpret_cast<uint32_t*>(og + (long long)qrow0 * p.o_rs + d) = pack_bf16x2(acc_o[dt][0] * inv0, acc_o[dt][1] * inv0);
+        if (qrow0 + 8 < p.Sq)
+            *reinterpret_cast<uint32_t*>(og + (long long)(qrow0 + 8) * p.o_rs + d) = pack_bf16x2(acc_o[dt][2] * inv1, acc_o[dt][3] * inv1);
+    }
+}
+
+template <int D, bool CAUSAL>
+static int launch_attn(const AttnParams& p, int B, cudaStream_t st) {
+    constexpr int SMEM = (ATT_BM + 4 * ATT_BN) * (D + 8) * 2;
+    static bool set = false;
+    if (!set) {
+        if (cudaFuncSetAttribute(attention_kernel<D, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess)
+            return GROMA_ERR_CUDA;
+        set = true;
+    }
+    dim3 grid((p.Sq + ATT_BM - 1) / ATT_BM, p.H, B);
+    attention_kernel<D, CAUSAL><<<grid, ATT_THREADS, SMEM, st>>>(p);
+    return GROMA_LAUNCH_CHECK();
+}
+
+}  // namespace gb
+using namespace gb;
+
+GROMA_API int32_t groma_attention(const void* q, int64_t q_bs, int64_t q_rs, const void* k, int64_t k_bs, int64_t k_hs,
+                                  int64_t k_rs, const void* v, int64_t v_bs, int64_t v_hs, int64_t v_rs, void* o,
+                                  int64_t o_bs, int64_t o_rs, const int32_t* kv_len, int32_t B, int32_t H, int32_t Sq,
+                                  int32_t Sk, int32_t D, int32_t causal, int32_t q_pos0, float scale, void* stream) {
+    if (!q || !k || !v || !o || B <= 0 || H <= 0 || Sq <= 0 || Sk <= 0) return GROMA_ERR_ARG;
+    if ((q_rs & 7) || (k_rs & 7) || (v_rs & 7) || (o_rs & 1) || (q_bs & 7) || (k_bs & 7) || (k_hs & 7) || (v_bs & 7) || (v_hs & 7))
+        return GROMA_ERR_ALIGN;
+    AttnParams p;
+    p.q = reinterpret_cast<const __nv_bfloat16*>(q); p.q_bs = q_bs; p.q_rs = q_rs;
+    p.k = reinterpret_cast<const __nv_bfloat16*>(k); p.k_bs = k_bs; p.k_hs = k_hs; p.k_rs = k_rs;
+    p.v = reinterpret_cast<const __nv_bfloat16*>(v); p.v_bs = v_bs; p.v_hs = v_hs; p.v_rs = v_rs;
+    p.o = reinterpret_cast<__nv_bfloat16*>(o); p.o_bs = o_bs; p.o_rs = o_rs;
+    p.kv_len = kv_len; p.Sq = Sq; p.Sk = Sk; p.H = H; p.q_pos0 = q_pos0;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (D == 128) return causal ? launch_attn<128, true>(p, B, st) : launch_attn<128, false>(p, B, st);
+    if (D == 64) return causal ? launch_attn<64, true>(p, B, st) : launch_attn<64, false>(p, B, st);
+    if (D == 32) return causal ? launch_attn<32, true>(p, B, st) : launch_attn<32, false>(p, B, st);
+    return GROMA_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,311 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:  D[M,N] = sum_taps A[M + off(tap), K] * B[N, tap*K + K]^T
+//   - operands are K-major bf16 in HBM, moved by TMA (128B swizzle) into a multi-stage shared-memory ring
+//   - one elected thread issues tcgen05.mma (cta_group::1, M=128, N=BN, K=16), fp32 accumulators live in TMEM
+//   - two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1
+//   - 4 epilogue warps: tcgen05.ld -> bias / activation / LayerScale / residual -> bf16|fp32 stores
+// "taps" turn the same kernel into an implicit-GEMM 3x3 convolution over zero-bordered flat NHWC maps
+// (each tap is a row shift of A and a K offset of B), see DESIGN.md "conv as shifted-row GEMM".
+#pragma once
+#include "ptx.cuh"
+
+namespace gb {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_MAX_TAPS = 27;
+constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+
+enum GemmAct : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_SWIGLU = 3 };
+enum GemmFlags : int {
+    GF_OUT_F32 = 1,       // out is fp32 (else bf16)
+    GF_BIAS_ALONG_M = 2,  // bias/gamma indexed by row (swap-AB calls)
+    GF_PARTIAL = 4,       // store raw fp32 accumulators to ws[split][m][n] (split-K / deferred epilogue)
+    GF_CONV_ROWS = 8,     // rows are pixels of zero-bordered [img][hp][wp] maps: skip border rows
+    GF_CONV_COMPACT = 16, // with GF_CONV_ROWS: write row index of the un-padded [img][h][w] layout
+};
+
+struct GemmParams {
+    CUtensorMap tma_a;  // [rows_a, K_total_a] bf16, box {64, 128}
+    CUtensorMap tma_b;  // [N, taps*K]        bf16, box {64, BN}
+    int M, N, K;        // K = reduction length per tap
+    int num_taps;
+    int a_row_off[GEMM_MAX_TAPS];  // row shift of A per tap (may be negative: TMA zero-fills OOB)
+    int split_k;                   // >=1; >1 requires GF_PARTIAL
+    int flags;
+    int act;
+    void* out;            // bf16 or fp32
+    long long ld_m, ld_n;  // element strides of out / residual
+    const float* bias;     // fp32 [N] (or [M]) or null
+    const float* gamma;    // fp32 LayerScale [N] (or [M]) or null: v *= gamma before residual
+    const __nv_bfloat16* residual;  // same strides as out, or null
+    float* ws;             // fp32 partials [split][M][N] when GF_PARTIAL
+    int conv_hp, conv_wp;  // padded map dims for GF_CONV_ROWS
+};
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+    static constexpr int B_BYTES = BN * GEMM_BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+    static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == ACT_GELU) return gelu_erf(v);
+    if (act == ACT_RELU) return fmaxf(v, 0.0f);
+    return v;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;       // [2]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+    const int n_tiles = (p.N + BN - 1) / BN;
+    const int kb_per_tap = (p.K + GEMM_BK - 1) / GEMM_BK;
+    const int total_iters = kb_per_tap * p.num_taps;
+    const int iters_per_split = (total_iters + p.split_k - 1) / p.split_k;
+    const int num_work = m_tiles * n_tiles * p.split_k;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tma_a);
+        tma_prefetch_desc(&p.tma_b);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < STAGES; ++i) {
+                mbar_init(&full_bar[i], 1);
+                mbar_init(&empty_bar[i], 1);
+            }
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&tfull_bar[i], 1);
+                mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<Cfg::TMEM_COLS>(tmem_holder);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+                const int split = w % p.split_k;
+                const int tile = w / p.split_k;
+                const int n_blk = tile % n_tiles, m_blk = tile / n_tiles;
+                const int it0 = split * iters_per_split;
+                const int it1 = min(total_iters, it0 + iters_per_split);
+                for (int it = it0; it < it1; ++it) {
+                    const int tap = it / kb_per_tap, kb = it - tap * kb_per_tap;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sb = sa + Cfg::A_BYTES;
+                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    tma_load_2d(sa, &p.tma_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM + p.a_row_off[tap]);
+                    tma_load_2d(sb, &p.tma_b, &full_bar[stage], tap * p.K + kb * GEMM_BK, n_blk * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+                const int split = w % p.split_k;
+                const int it0 = split * iters_per_split;
+                const int it1 = min(total_iters, it0 + iters_per_split);
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int it = it0; it < it1; ++it) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t sb = sa + Cfg::A_BYTES;
+                    const uint64_t da = make_sw128_kmajor_desc(sa);
+                    const uint64_t db = make_sw128_kmajor_desc(sb);
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k) {
+                        // advancing 16 bf16 (=32 B) along K inside the swizzle atom: +2 in 16-byte units
+                        umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it > it0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue warps (2..5) =====================
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const bool out_f32 = (p.flags & GF_OUT_F32) != 0;
+        const bool bias_m = (p.flags & GF_BIAS_ALONG_M) != 0;
+        const bool partial = (p.flags & GF_PARTIAL) != 0;
+        for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+            const int split = w % p.split_k;
+            const int tile = w / p.split_k;
+            const int n_blk = tile % n_tiles, m_blk = tile / n_tiles;
+            const int it0 = split * iters_per_split;
+            const bool has_work = it0 < total_iters;  // an empty split contributes zeros
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const int row = m_blk * GEMM_BM + q * 32 + lane;
+            bool row_ok = row < p.M;
+            long long out_row = row;
+            if (p.flags & GF_CONV_ROWS) {
+                const int per_img = p.conv_hp * p.conv_wp;
+                const int img = row / per_img, rem = row - img * per_img;
+                const int y = rem / p.conv_wp, x = rem - y * p.conv_wp;
+                row_ok = row_ok && y >= 1 && y <= p.conv_hp - 2 && x >= 1 && x <= p.conv_wp - 2;
+                if (p.flags & GF_CONV_COMPACT)
+                    out_row = (long long)img * (p.conv_hp - 2) * (p.conv_wp - 2) + (long long)(y - 1) * (p.conv_wp - 2) + (x - 1);
+            }
+            constexpr int CHUNK = (BN >= 32) ? 32 : 16;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += CHUNK) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + c0);
+                __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent stores below
+                if (CHUNK == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+                tmem_ld_wait();
+                const int n0 = n_blk * BN + c0;
+                if (!row_ok || n0 >= p.N) continue;
+                if (!has_work) {
+#pragma unroll
+                    for (int j = 0; j < CHUNK; ++j) v[j] = 0u;
+                }
+                if (partial) {
+                    float* dst = p.ws + ((long long)split * p.M + out_row) * p.N + n0;
+                    if ((p.N & 3) == 0 && n0 + CHUNK <= p.N) {
+#pragma unroll
+                        for (int j = 0; j < CHUNK; j += 4)
+                            *reinterpret_cast<uint4*>(dst + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+                        _Pragma("unroll") for (int j = 0; j < CHUNK; ++j) if (n0 + j < p.N) dst[j] = __uint_as_float(v[j]);
+                    }
+                    continue;
+                }
+                // ---- full epilogue
+                float f[32];
+                const float bm = (bias_m && p.bias) ? p.bias[row] : 0.0f;
+                const float gm = (bias_m && p.gamma) ? p.gamma[row] : 1.0f;
+#pragma unroll
+                for (int j = 0; j < CHUNK; ++j) {
+                    float x = __uint_as_float(v[j]);
+                    const int n = n0 + j;
+                    if (p.bias) x += bias_m ? bm : (n < p.N ? p.bias[n] : 0.0f);
+                    f[j] = x;
+                }
+                if (p.act == ACT_SWIGLU) {
+                    // columns (2j, 2j+1) = (gate_j, up_j): out[:, n/2] = silu(gate) * up
+                    const int no0 = n0 >> 1;
+                    const int NO = p.N >> 1;
+                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ld_m + no0;
+                    float g[16];
+#pragma unroll
+                    for (int j = 0; j < CHUNK / 2; ++j) g[j] = silu(f[2 * j]) * f[2 * j + 1];
+                    if (p.ld_n == 1 && (p.ld_m & 7) == 0 && (no0 & 7) == 0 && no0 + CHUNK / 2 <= NO) {
+#pragma unroll
+                        for (int j = 0; j < CHUNK / 2; j += 8)
+                            *reinterpret_cast<uint4*>(dst + j) =
+                                make_uint4(pack_bf16x2(g[j], g[j + 1]), pack_bf16x2(g[j + 2], g[j + 3]),
+                                           pack_bf16x2(g[j + 4], g[j + 5]), pack_bf16x2(g[j + 6], g[j + 7]));
+                    } else {
+                        _Pragma("unroll") for (int j = 0; j < CHUNK / 2; ++j) if (no0 + j < NO) dst[(long long)j * p.ld_n] = __float2bfloat16_rn(g[j]);
+                    }
+                    continue;
+                }
+#pragma unroll
+                for (int j = 0; j < CHUNK; ++j) {
+                    float x = apply_act(f[j], p.act);
+                    const int n = n0 + j;
+                    if (p.gamma) x *= bias_m ? gm : (n < p.N ? p.gamma[n] : 1.0f);
+                    f[j] = x;
+                }
+                const long long obase = out_row * p.ld_m + (long long)n0 * p.ld_n;
+                const bool vec_ok = p.ld_n == 1 && (p.ld_m & 7) == 0 && (n0 & 7) == 0 && n0 + CHUNK <= p.N;
+                if (p.residual) {
+                    const __nv_bfloat16* r = p.residual + obase;
+                    if (vec_ok) {
+#pragma unroll
+                        for (int j = 0; j < CHUNK; j += 8) {
+                            const uint4 rv = *reinterpret_cast<const uint4*>(r + j);
+                            const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const float2 rf = __bfloat1622float2(r2[t]);
+                                f[j + 2 * t] += rf.x;
+                                f[j + 2 * t + 1] += rf.y;
+                            }
+                        }
+                    } else {
+                        _Pragma("unroll") for (int j = 0; j < CHUNK; ++j) if (n0 + j < p.N) f[j] += __bfloat162float(r[(long long)j * p.ld_n]);
+                    }
+                }
+                if (out_f32) {
+                    float* dst = reinterpret_cast<float*>(p.out) + obase;
+                    if (p.ld_n == 1 && (p.ld_m & 3) == 0 && (n0 & 3) == 0 && n0 + CHUNK <= p.N) {
+#pragma unroll
+                        for (int j = 0; j < CHUNK; j += 4)
+                            *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    } else {
+                        _Pragma("unroll") for (int j = 0; j < CHUNK; ++j) if (n0 + j < p.N) dst[(long long)j * p.ld_n] = f[j];
+                    }
+                } else {
+                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + obase;
+                    if (vec_ok) {
+#pragma unroll
+                        for (int j = 0; j < CHUNK; j += 8)
+                            *reinterpret_cast<uint4*>(dst + j) =
+                                make_uint4(pack_bf16x2(f[j], f[j + 1]), pack_bf16x2(f[j + 2], f[j + 3]),
+                                           pack_bf16x2(f[j + 4], f[j + 5]), pack_bf16x2(f[j + 6], f[j + 7]));
+                    } else {
+                        _Pragma("unroll") for (int j = 0; j < CHUNK; ++j) if (n0 + j < p.N) dst[(long long)j * p.ld_n] = __float2bfloat16_rn(f[j]);
+                    }
+                }
+            }
+            // release this accumulator stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    }
+}
+
+}  // namespace gb

@@ -1,0 +1,104 @@
+// Multi-scale deformable attention sampling (Deformable-DETR).  Follows the SenseTime kernel the reference binds
+// (mmcv/ops/csrc/common/cuda/ms_deform_attn_cuda_kernel.cuh:19-66,203-256) and its PyTorch twin
+// (mmcv/ops/multi_scale_deform_attn.py:93-150): bilinear taps at loc*size-0.5 with zero padding, weighted by the
+// per-head softmax over (levels x points).  Fused here: softmax of the attention logits and the
+// reference-point + offset location math (modeling_deformable_detr.py:586-610), so the only HBM traffic is
+// value (bf16), the fp32 projection row, the reference points and the bf16 output.
+// One warp per (batch, query, head); lane = channel of the 32-wide head -> every tap is one 64-byte coalesced read.
+#include "ptx.cuh"
+#include "capi_common.h"
+
+namespace gb {
+
+struct MsdaParams {
+    const __nv_bfloat16* value;  // [B, S, nH, 32]
+    const float* proj;           // [B*Q, nH*L*P*2 + nH*L*P]  (sampling offsets | attention logits)
+    const float* ref;            // [B, Q, ref_dim]  (ref_dim 2: per-level normalised xy shared by all levels; 4: cxcywh)
+    __nv_bfloat16* out;          // [B, Q, nH*32]
+    int B, Q, S, nH, L, P, ref_dim;
+    int lvl_h[4], lvl_w[4], lvl_start[4];
+};
+
+__global__ void msda_kernel(const MsdaParams p) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long total = (long long)p.B * p.Q * p.nH;
+    if (warp_global >= total) return;
+    const int head = warp_global % p.nH;
+    const long long bq = warp_global / p.nH;
+    const int b = bq / p.Q;
+    const int LP = p.L * p.P;
+    const int n_off = p.nH * LP * 2;
+    const float* prow = p.proj + bq * (long long)(n_off + p.nH * LP);
+    const float* off = prow + head * LP * 2;
+    const float* logit = prow + n_off + head * LP;
+    const float* ref = p.ref + bq * p.ref_dim;
+
+    // softmax over L*P logits (<= 16), every lane computes it redundantly (broadcast loads)
+    float mx = -INFINITY;
+    for (int i = 0; i < LP; ++i) mx = fmaxf(mx, logit[i]);
+    float den = 0.f;
+    for (int i = 0; i < LP; ++i) den += __expf(logit[i] - mx);
+    const float inv_den = 1.f / den;
+
+    const __nv_bfloat16* vbase = p.value + ((long long)b * p.S) * p.nH * 32 + head * 32 + lane;
+    const long long vstride = (long long)p.nH * 32;
+    float acc = 0.f;
+    for (int l = 0; l < p.L; ++l) {
+        const int H = p.lvl_h[l], W = p.lvl_w[l];
+        const __nv_bfloat16* vl = vbase + (long long)p.lvl_start[l] * vstride;
+        for (int k = 0; k < p.P; ++k) {
+            const int i = l * p.P + k;
+            const float ox = off[i * 2], oy = off[i * 2 + 1];
+            float lx, ly;
+            if (p.ref_dim == 2) {
+                lx = ref[0] + ox / (float)W;
+                ly = ref[1] + oy / (float)H;
+            } else {
+                lx = ref[0] + ox / (float)p.P * ref[2] * 0.5f;
+                ly = ref[1] + oy / (float)p.P * ref[3] * 0.5f;
+            }
+            const float w_attn = __expf(logit[i] - mx) * inv_den;
+            const float h_im = ly * H - 0.5f, w_im = lx * W - 0.5f;
+            if (h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W) {
+                const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+                const int h_high = h_low + 1, w_high = w_low + 1;
+                const float lh = h_im - h_low, lw = w_im - w_low, hh = 1.f - lh, hw = 1.f - lw;
+                float v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f;
+                if (h_low >= 0 && w_low >= 0) v1 = __bfloat162float(vl[(long long)(h_low * W + w_low) * vstride]);
+                if (h_low >= 0 && w_high <= W - 1) v2 = __bfloat162float(vl[(long long)(h_low * W + w_high) * vstride]);
+                if (h_high <= H - 1 && w_low >= 0) v3 = __bfloat162float(vl[(long long)(h_high * W + w_low) * vstride]);
+                if (h_high <= H - 1 && w_high <= W - 1) v4 = __bfloat162float(vl[(long long)(h_high * W + w_high) * vstride]);
+                acc += w_attn * (hh * hw * v1 + hh * lw * v2 + lh * hw * v3 + lh * lw * v4);
+            }
+        }
+    }
+    p.out[bq * (long long)(p.nH * 32) + head * 32 + lane] = __float2bfloat16_rn(acc);
+}
+
+}  // namespace gb
+using namespace gb;
+
+// C-ABI twin of mmcv `ms_deform_attn_forward` (mmcv/ops/csrc/pytorch/pybind.cpp:162,765) with the softmax and
+// location arithmetic folded in; head_dim fixed at 32 (d_model 256 / 8 heads).
+GROMA_API int32_t groma_msda_forward(const void* value, const float* proj, const float* ref, void* out, int32_t B,
+                                     int32_t Q, int32_t S, int32_t n_heads, int32_t n_levels, int32_t n_points,
+                                     int32_t ref_dim, const int32_t* level_hw, const int32_t* level_start, void* stream) {
+    if (!value || !proj || !ref || !out || !level_hw || !level_start) return GROMA_ERR_ARG;
+    if (n_levels < 1 || n_levels > 4 || n_points < 1 || n_levels * n_points > 16 || (ref_dim != 2 && ref_dim != 4))
+        return GROMA_ERR_UNSUPPORTED;
+    MsdaParams p;
+    p.value = reinterpret_cast<const __nv_bfloat16*>(value); p.proj = proj; p.ref = ref;
+    p.out = reinterpret_cast<__nv_bfloat16*>(out);
+    p.B = B; p.Q = Q; p.S = S; p.nH = n_heads; p.L = n_levels; p.P = n_points; p.ref_dim = ref_dim;
+    for (int l = 0; l < 4; ++l) {
+        p.lvl_h[l] = l < n_levels ? level_hw[2 * l] : 0;
+        p.lvl_w[l] = l < n_levels ? level_hw[2 * l + 1] : 0;
+        p.lvl_start[l] = l < n_levels ? level_start[l] : 0;
+    }
+    const long long warps = (long long)B * Q * n_heads;
+    const int threads = 256;
+    const long long blocks = (warps * 32 + threads - 1) / threads;
+    msda_kernel<<<(unsigned)blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    return GROMA_LAUNCH_CHECK();
+}

@@ -1,0 +1,166 @@
+/* groma_b200 -- C ABI of the B200-native Groma forward hot path (libgroma_b200.so, sm_100a).
+ *
+ * Conventions (every entry point):
+ *   - returns int32_t status: 0 = GROMA_OK, otherwise a GROMA_ERR_* code; no exceptions cross the boundary
+ *   - all pointers are DEVICE pointers unless a parameter says "host"; outputs and workspaces are caller-owned
+ *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued on it, nothing synchronises, nothing allocates
+ *   - matrices are row-major bf16 (uint16 storage) unless stated; bias / norm / scale vectors are fp32
+ *   - thread-compatible: no global mutable state beyond one-time kernel attribute setup
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to the FoundationVision/Groma tree;
+ * $HF = transformers 4.32 as pinned by the reference's pyproject.toml:19).
+ */
+#ifndef GROMA_B200_H
+#define GROMA_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GROMA_OK 0
+#define GROMA_ERR_ARG 1
+#define GROMA_ERR_ALIGN 2
+#define GROMA_ERR_CUDA 3
+#define GROMA_ERR_DRIVER 4
+#define GROMA_ERR_TMA_ENCODE 5
+#define GROMA_ERR_UNSUPPORTED 6
+
+/* epilogue activation / flags of groma_gemm_bf16 */
+#define GROMA_ACT_NONE 0
+#define GROMA_ACT_GELU 1   /* erf GELU (nn.GELU default) */
+#define GROMA_ACT_RELU 2
+#define GROMA_ACT_SWIGLU 3 /* columns (2j,2j+1) = (gate_j, up_j) -> out[:, j] = silu(gate)*up ; N_out = N/2 */
+#define GROMA_GF_OUT_F32 1
+#define GROMA_GF_BIAS_ALONG_M 2
+#define GROMA_GF_PARTIAL 4
+#define GROMA_GF_CONV_ROWS 8
+#define GROMA_GF_CONV_COMPACT 16
+
+/* D[M,N] = sum_{t<num_taps} A[m + a_row_off[t], 0:K] . B[n, t*K : (t+1)*K]   (+ bias, act, *gamma, + residual)
+ * tcgen05/TMEM/TMA GEMM.  Replaces every torch.nn.Linear / nn.Conv2d(1x1, 3x3 pad 1) call on the path:
+ *   groma/model/groma.py:112-119,389-401 ; groma/model/roi_align.py:128-143,251-264 ; groma/model/ddetr.py:147-151 ;
+ *   $HF/models/{dinov2,llama,deformable_detr}/modeling_*.py Linear layers (cuBLAS / cuDNN in the reference).
+ * A: [a_rows, lda] bf16, B: [b_rows, ldb] bf16 (lda, ldb multiples of 8; pointers 16-byte aligned).
+ * num_taps > 1 = implicit-GEMM convolution over zero-bordered flat NHWC maps (a_row_off = tap row shifts, host array).
+ * out[m*ld_m + n*ld_n] bf16 (or fp32 with GROMA_GF_OUT_F32); bias/gamma fp32 per column (per row with BIAS_ALONG_M);
+ * residual bf16 with the strides of out.  GROMA_GF_PARTIAL: raw fp32 accumulators to ws[split][M][N] (split_k >= 1).
+ * GROMA_GF_CONV_ROWS: rows are pixels of [img][conv_hp][conv_wp] maps, border rows are not written;
+ * with GROMA_GF_CONV_COMPACT the row index is that of the un-padded [img][hp-2][wp-2] layout.
+ * block_n: 0 = auto, else 16/32/64/128/256. */
+int32_t groma_gemm_bf16(const void* A, int64_t a_rows, int64_t lda, const void* B, int64_t b_rows, int64_t ldb,
+                        int32_t M, int32_t N, int32_t K, int32_t num_taps, const int32_t* a_row_off /*host*/,
+                        void* out, int64_t ld_m, int64_t ld_n, int32_t flags, int32_t act, const float* bias,
+                        const float* gamma, const void* residual, float* ws, int32_t split_k, int32_t conv_hp,
+                        int32_t conv_wp, int32_t block_n, void* stream);
+
+/* out = epilogue(sum_s ws[s][M][N]) -- the deferred epilogue of a GROMA_GF_PARTIAL GEMM (same chain as above). */
+int32_t groma_splitk_reduce(const float* ws, int32_t splits, int32_t M, int32_t N, int32_t act, int32_t flags,
+                            const float* bias, const float* gamma, const void* residual, void* out, int64_t ld_m,
+                            int64_t ld_n, void* stream);
+
+/* softmax(QK^T*scale + mask)V, bf16, head_dim 32/64/128, online softmax, fp32 accumulate.
+ * Replaces $HF/models/llama/modeling_llama.py:199-289 (eager attention, causal + key padding),
+ * $HF/models/dinov2/modeling_dinov2.py:153-179 and $HF/models/deformable_detr/modeling_deformable_detr.py:453-516.
+ * q[b*q_bs + i*q_rs + h*D + d], k[b*k_bs + h*k_hs + j*k_rs + d] (v alike), o[b*o_bs + i*o_rs + h*D + d].
+ * causal: key j visible to query i iff j <= q_pos0 + i.  kv_len (optional, int32[B]): keys >= kv_len[b] masked. */
+int32_t groma_attention(const void* q, int64_t q_bs, int64_t q_rs, const void* k, int64_t k_bs, int64_t k_hs,
+                        int64_t k_rs, const void* v, int64_t v_bs, int64_t v_hs, int64_t v_rs, void* o, int64_t o_bs,
+                        int64_t o_rs, const int32_t* kv_len, int32_t B, int32_t H, int32_t Sq, int32_t Sk, int32_t D,
+                        int32_t causal, int32_t q_pos0, float scale, void* stream);
+
+/* y = w * bf16(h * rsqrt(mean(h^2)+eps)), h = bf16(x + residual) (h_out optional).  LlamaRMSNorm,
+ * $HF/models/llama/modeling_llama.py:53-70 (+ the residual add of :292-340). */
+int32_t groma_rmsnorm(const void* x, const void* residual, const float* w, void* y, void* h_out, int64_t rows,
+                      int32_t dim, float eps, void* stream);
+
+/* y = LayerNorm(x (+ residual)) * w + b over the last dim.  nn.LayerNorm call sites: modeling_dinov2.py:356-372,
+ * modeling_deformable_detr.py:699-706,782-803 (post-LN), groma/model/ddetr.py:25-45 (channel LN == LN over NHWC C),
+ * groma/model/roi_align.py:254-261, ddetr_transformer.py:311-314. */
+int32_t groma_layernorm(const void* x, const void* residual, const float* w, const float* b, void* y, int64_t rows,
+                        int32_t dim, float eps, int64_t x_row_stride, int64_t y_row_stride, void* stream);
+
+/* y = relu(GroupNorm_G(x)) over NHWC [B, P, C]; mmcv ConvModule norm+act (mmcv/cnn/bricks/conv_module.py:196-206)
+ * as used by groma/model/roi_align.py:133-143.  part: fp32 scratch [B*chunks*G*2]; stats: fp32 [B*G*2] (mean, rstd). */
+int32_t groma_groupnorm_relu(const void* x, const float* gamma, const float* beta, void* y, float* part, float* stats,
+                             int32_t B, int64_t P, int32_t C, int32_t G, float eps, int32_t chunks, void* stream);
+
+/* Multi-scale deformable attention forward; twin of mmcv `ms_deform_attn_forward`
+ * (mmcv/ops/csrc/pytorch/pybind.cpp:162,765; kernel common/cuda/ms_deform_attn_cuda_kernel.cuh:203-256) with the
+ * softmax over (levels*points) and the sampling-location arithmetic of modeling_deformable_detr.py:586-610 fused in.
+ * value [B,S,nH,32] bf16; proj [B*Q, nH*L*P*2 + nH*L*P] fp32 (offsets | logits); ref [B,Q,ref_dim] fp32;
+ * out [B,Q,nH*32] bf16; level_hw host int32[2L] (h,w), level_start host int32[L]. */
+int32_t groma_msda_forward(const void* value, const float* proj, const float* ref, void* out, int32_t B, int32_t Q,
+                           int32_t S, int32_t n_heads, int32_t n_levels, int32_t n_points, int32_t ref_dim,
+                           const int32_t* level_hw /*host*/, const int32_t* level_start /*host*/, void* stream);
+
+/* RoIAlign forward (avg, aligned flag); twin of mmcv `roi_align_forward` (pybind.cpp:191,611; kernel
+ * common/cuda/roi_align_cuda_kernel.cuh:17-108).  input NHWC bf16 [N,H,W,C]; rois fp32 [K,5] (batch, x1,y1,x2,y2);
+ * output [K, ph+2p, pw+2p, C] bf16 with p = out_pad (0/1) zero border. */
+int32_t groma_roi_align_forward(const void* input, const float* rois, void* output, int32_t K, int32_t C, int32_t H,
+                                int32_t W, int32_t pooled_h, int32_t pooled_w, float spatial_scale,
+                                int32_t sampling_ratio, int32_t aligned, int32_t out_pad, void* stream);
+
+/* Batched greedy NMS; twin of mmcv `nms` (pybind.cpp:175,596; nms_cuda_kernel.cuh:18-74, nms_cuda.cu:5-54) plus the
+ * score filter / max_num of mmcv/ops/nms.py:14-33, for all images of groma/model/groma.py:257-280 in one launch.
+ * boxes [B,N,4] xyxy fp32, scores [B,N] fp32, counts int32[B] (optional valid prefix length per image).
+ * keep int64 [B,max_out] (original indices, score order, -1 padded); num_keep int32[B];
+ * argmax_idx int32[B] = first index of the max score (the reference's fallback when nothing is kept). */
+int32_t groma_nms_batched(const float* boxes, const float* scores, const int32_t* counts, int32_t B, int32_t N,
+                          float iou_threshold, float score_threshold, int32_t offset, int32_t max_num, int64_t* keep,
+                          int32_t max_out, int32_t* num_keep, int32_t* argmax_idx, void* stream);
+
+/* torch.topk(scores, k, dim=1)[1] (ddetr_transformer.py:556): indices of the k largest, descending. */
+int32_t groma_topk_desc(const float* scores, int64_t ld, int32_t B, int32_t N, int32_t k, int64_t* out_idx, void* stream);
+
+/* Two-stage proposal gather + sigmoid + sine embedding (ddetr_transformer.py:432-446,556-566). */
+int32_t groma_ddetr_select(const float* delta, const float* proposals, const int64_t* topk, float* ref_out,
+                           void* pos_out, int32_t B, int32_t S, int32_t k, int32_t num_pos_feats, void* stream);
+
+/* Final box/score heads (ddetr_transformer.py:696-715 restricted to what inference reads, groma.py:246-249,268). */
+int32_t groma_ddetr_finalize(const float* d4, const float* d5, const float* ref0, const float* coco, const float* sa1b,
+                             float* pred_cxcywh, float* pred_xyxy, float* score, int32_t B, int32_t Q,
+                             int64_t out_stride_boxes, int64_t out_stride_scores, void* stream);
+
+/* zero rows of x [B,S,D] where valid[s]==0 (ddetr_transformer.py:424-426). */
+int32_t groma_mask_rows(void* x, const uint8_t* valid, int32_t B, int32_t S, int32_t D, void* stream);
+
+/* Region-encoder resampling (groma/model/roi_align.py:118-126,215-228 and :150-178). */
+int32_t groma_upsample_coords(const void* tokens, int32_t skip, int32_t g, int32_t C, void* out, int32_t B, int32_t Ho,
+                              int32_t Wo, int32_t ld, const float* xs, const float* ys, void* stream);
+int32_t groma_fuse_shuffle(const void* tar, const void* top, const void* down, void* out, int32_t B, int32_t C,
+                           int32_t Ht, int32_t Wt, int32_t Htop, int32_t Wtop, int32_t Hdn, int32_t Wdn, void* stream);
+
+/* DINOv2 embeddings (modeling_dinov2.py:57-149): im2col of 14x14 patches and CLS/pos-embed assembly. */
+int32_t groma_vit_patchify(const float* images, void* patches, int32_t B, int32_t S, int32_t ld, void* stream);
+int32_t groma_vit_embed(const void* patch, const float* cls, const float* pos, void* out, int32_t B, int32_t NP,
+                        int32_t C, void* stream);
+
+/* groma.py:227-242: mean of the last hidden states (CLS dropped) and the 2x2 space-to-depth token merge. */
+int32_t groma_mean_tokens(const void* a0, const void* a1, const void* a2, const void* a3, int32_t n, void* out,
+                          int32_t B, int32_t T, int32_t C, int32_t skip, void* stream);
+int32_t groma_space_to_depth(const void* in, void* out, int32_t B, int32_t g, int32_t C, void* stream);
+
+/* groma.py:165-174,360-369: split-vocabulary embedding lookup and visual-token splice (row gather / scatter). */
+int32_t groma_gather_rows(const int64_t* idx, const void* t0, const void* t1, int64_t split, void* out, int64_t n,
+                          int32_t D, void* stream);
+int32_t groma_scatter_rows(const int64_t* idx, const void* src, void* out, int64_t n, int32_t D, void* stream);
+
+int32_t groma_add(const void* a, const void* b, void* c, int64_t n, void* stream);
+int32_t groma_add_bcast(const void* a, const void* b, void* c, int64_t rows, int64_t period, int32_t D, void* stream);
+
+/* rotate-half RoPE on fused QKV rows + KV-cache append (modeling_llama.py:138-168,225-289). */
+int32_t groma_rope_kv(const void* qkv, void* q_out, void* cache_k, void* cache_v, const float* cos_t,
+                      const float* sin_t, int32_t B, int32_t T, int32_t H, int32_t D, int32_t pos0, int64_t ctx_cap,
+                      void* stream);
+
+/* greedy next-token argmax over fp32 logits (HF greedy_search). */
+int32_t groma_argmax(const float* logits, int64_t* out, int32_t rows, int32_t V, int64_t ld, void* stream);
+
+int32_t groma_cast_f32_bf16(const float* a, void* b, int64_t n, void* stream);
+int32_t groma_cast_bf16_f32(const void* a, float* b, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GROMA_B200_H */

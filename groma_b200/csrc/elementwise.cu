@@ -162,8 +162,9 @@ __global__ void add_bcast_kernel(const __nv_bfloat16* __restrict__ a, const __nv
 __global__ void rope_kv_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ q_out,
                                __nv_bfloat16* __restrict__ cache_k, __nv_bfloat16* __restrict__ cache_v,
                                const float* __restrict__ cos_t, const float* __restrict__ sin_t, int B, int T, int H,
-                               int D, int pos0, long long ctx_cap) {
+                               int D, int pos0, const int* __restrict__ pos_ptr, long long ctx_cap) {
     const int half = D / 2;
+    if (pos_ptr) pos0 = *pos_ptr;
     const long long total = (long long)B * T * H * half;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int j = i % half;
@@ -187,6 +188,28 @@ __global__ void rope_kv_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloa
         cache_v[co + j] = vp[j];
         cache_v[co + j + half] = vp[j + half];
     }
+}
+
+// ---- tiny-K linear in fp32: out[m,n] = act(sum_k x[m,k]*w[n,k] + b[n]) -> bf16  (roi_align.py:255 Linear(4,256))
+__global__ void linear_smallk_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                     __nv_bfloat16* __restrict__ out, long long M, int N, int K, int relu) {
+    const long long total = M * N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int n = i % N;
+        const long long m = i / N;
+        float acc = 0.f;
+        for (int k = 0; k < K; ++k) acc += x[m * K + k] * w[(long long)n * K + k];
+        if (b) acc += b[n];
+        if (relu) acc = fmaxf(acc, 0.f);
+        out[i] = __float2bfloat16_rn(acc);
+    }
+}
+
+// ---- decode bookkeeping on the device (so the step can live in a CUDA graph): pos += 1, kv_len[b] += 1
+__global__ void decode_advance_kernel(int* pos, int* kv_len, int B) {
+    const int i = threadIdx.x;
+    if (i == 0) *pos += 1;
+    if (i < B) kv_len[i] += 1;
 }
 
 // ---- greedy argmax over fp32 logits [rows, V] -> int64 ids (first maximal index, like torch.argmax)
@@ -291,11 +314,11 @@ GROMA_API int32_t groma_add_bcast(const void* a, const void* b, void* c, int64_t
 }
 GROMA_API int32_t groma_rope_kv(const void* qkv, void* q_out, void* cache_k, void* cache_v, const float* cos_t,
                                 const float* sin_t, int32_t B, int32_t T, int32_t H, int32_t D, int32_t pos0,
-                                int64_t ctx_cap, void* stream) {
+                                const int32_t* pos_ptr, int64_t ctx_cap, void* stream) {
     if (!qkv || !q_out || !cache_k || !cache_v || !cos_t || !sin_t || (D & 1)) return GROMA_ERR_ARG;
-    if (pos0 + T > ctx_cap) return GROMA_ERR_ARG;
+    if (!pos_ptr && pos0 + T > ctx_cap) return GROMA_ERR_ARG;
     rope_kv_kernel<<<grid_for((long long)B * T * H * (D / 2), 256), 256, 0, ST>>>(
-        CBF(qkv), BF(q_out), BF(cache_k), BF(cache_v), cos_t, sin_t, B, T, H, D, pos0, ctx_cap);
+        CBF(qkv), BF(q_out), BF(cache_k), BF(cache_v), cos_t, sin_t, B, T, H, D, pos0, pos_ptr, ctx_cap);
     return GROMA_LAUNCH_CHECK();
 }
 GROMA_API int32_t groma_argmax(const float* logits, int64_t* out, int32_t rows, int32_t V, int64_t ld, void* stream) {
@@ -311,5 +334,18 @@ GROMA_API int32_t groma_cast_f32_bf16(const float* a, void* b, int64_t n, void* 
 GROMA_API int32_t groma_cast_bf16_f32(const void* a, float* b, int64_t n, void* stream) {
     if (!a || !b) return GROMA_ERR_ARG;
     bf16_to_f32_kernel<<<grid_for(n, 256), 256, 0, ST>>>(CBF(a), b, n);
+    return GROMA_LAUNCH_CHECK();
+}
+
+GROMA_API int32_t groma_linear_smallk(const float* x, const float* w, const float* b, void* out, int64_t M, int32_t N,
+                                      int32_t K, int32_t relu, void* stream) {
+    if (!x || !w || !out || K <= 0 || K > 64) return GROMA_ERR_ARG;
+    if (M == 0) return GROMA_OK;
+    linear_smallk_kernel<<<grid_for(M * N, 256), 256, 0, ST>>>(x, w, b, BF(out), M, N, K, relu);
+    return GROMA_LAUNCH_CHECK();
+}
+GROMA_API int32_t groma_decode_advance(int32_t* pos, int32_t* kv_len, int32_t B, void* stream) {
+    if (!pos || !kv_len || B <= 0 || B > 1024) return GROMA_ERR_ARG;
+    decode_advance_kernel<<<1, ((B + 31) / 32) * 32, 0, ST>>>(pos, kv_len, B);
     return GROMA_LAUNCH_CHECK();
 }

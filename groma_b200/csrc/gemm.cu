@@ -69,9 +69,22 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, i
                                      const float* __restrict__ bias, const float* __restrict__ gamma,
                                      const __nv_bfloat16* __restrict__ residual, void* __restrict__ out, long long ld_m,
                                      long long ld_n) {
-    const long long total = (long long)M * (act == ACT_SWIGLU ? N / 2 : N);
+    const bool bias_m0 = flags & GF_BIAS_ALONG_M;
+    const long long total = (act == ACT_SWIGLU) ? (bias_m0 ? (long long)(M / 2) * N : (long long)M * (N / 2)) : (long long)M * N;
     const bool bias_m = flags & GF_BIAS_ALONG_M;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        if (act == ACT_SWIGLU && bias_m) {
+            // swap-AB layout: ws[s][M = 2*I rows (gate_j, up_j interleaved)][N = tokens] -> out[token, j]
+            const int t = i % N;
+            const long long j = i / N;  // i in [0, (M/2)*N)
+            float g = 0.f, u = 0.f;
+            for (int s2 = 0; s2 < splits; ++s2) {
+                g += ws[((long long)s2 * M + 2 * j) * N + t];
+                u += ws[((long long)s2 * M + 2 * j + 1) * N + t];
+            }
+            reinterpret_cast<__nv_bfloat16*>(out)[j * ld_m + t * ld_n] = __float2bfloat16_rn(silu(g) * u);
+            continue;
+        }
         if (act == ACT_SWIGLU) {
             const int NO = N / 2;
             const int m = i / NO, j = i - (long long)m * NO;
@@ -158,7 +171,7 @@ GROMA_API int32_t groma_splitk_reduce(const float* ws, int32_t splits, int32_t M
                                        int32_t flags, const float* bias, const float* gamma, const void* residual,
                                        void* out, int64_t ld_m, int64_t ld_n, void* stream) {
     if (!ws || !out || splits < 1 || M <= 0 || N <= 0) return GROMA_ERR_ARG;
-    const long long total = (long long)M * (act == ACT_SWIGLU ? N / 2 : N);
+    const long long total = (long long)M * N;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     splitk_reduce_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(

@@ -1,0 +1,500 @@
+"""GromaEngine -- host-side orchestration of the B200 forward path.
+
+Holds the packed weight arena (bf16 matrices in the layouts the kernels want, fp32 vectors) and sequences the C-ABI
+kernels of libgroma_b200.so for: DINOv2 encoder -> image tokens -> Deformable-DETR proposer -> region selection (NMS on
+device, randperm on the host CPU RNG) -> region encoder -> LLaMA prefill / decode.  PyTorch provides device memory and
+streams only.  Stage boundaries and rounding points are listed in DESIGN.md; the reference functions each stage
+replaces are cited at the methods (paths relative to the FoundationVision/Groma tree).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+from . import ops as G
+from .config import PathConfig
+
+
+def _cat(*ts):
+    return torch.cat(list(ts), 0)
+
+
+class GromaEngine:
+    def __init__(self, cfg: PathConfig, state_dict: Dict[str, torch.Tensor], device: str = "cuda"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("GromaEngine needs a CUDA device: the B200 path has no CPU fallback")
+        self.cfg = cfg
+        self.dev = torch.device(device)
+        self.w: Dict[str, torch.Tensor] = {}
+        self._pack(state_dict)
+        self._constants()
+        self.kv = None
+        self.stages: Dict[str, torch.Tensor] = {}
+        self.keep_stages = False
+
+    # ------------------------------------------------------------------------------------------ weights
+    def _mat(self, t: torch.Tensor) -> torch.Tensor:
+        return t.to(self.dev).to(torch.bfloat16).contiguous()
+
+    def _vec(self, t: torch.Tensor) -> torch.Tensor:
+        return t.to(self.dev).to(torch.float32).contiguous()
+
+    def _pack(self, sd: Dict[str, torch.Tensor]):
+        cfg, w = self.cfg, self.w
+        H, D, T = cfg.vit_hidden, cfg.d_model, cfg.llm_hidden
+        ve = "perceiver.vis_encoder."
+        pw = sd[ve + "embeddings.patch_embeddings.projection.weight"].reshape(H, -1).float()
+        self.patch_ld = ((pw.shape[1] + 7) // 8) * 8
+        pwp = torch.zeros(H, self.patch_ld)
+        pwp[:, :pw.shape[1]] = pw
+        w["vit.patch.w"], w["vit.patch.b"] = self._mat(pwp), self._vec(sd[ve + "embeddings.patch_embeddings.projection.bias"])
+        w["vit.cls"] = self._vec(sd[ve + "embeddings.cls_token"].reshape(-1))
+        w["vit.pos"] = self._vec(self._interp_pos(sd[ve + "embeddings.position_embeddings"].float()))
+        for i in range(cfg.vit_layers):
+            p, o = f"{ve}encoder.layer.{i}.", f"vit.{i}."
+            w[o + "ln1.w"], w[o + "ln1.b"] = self._vec(sd[p + "norm1.weight"]), self._vec(sd[p + "norm1.bias"])
+            w[o + "qkv.w"] = self._mat(_cat(*[sd[p + f"attention.attention.{n}.weight"] for n in ("query", "key", "value")]))
+            w[o + "qkv.b"] = self._vec(_cat(*[sd[p + f"attention.attention.{n}.bias"] for n in ("query", "key", "value")]))
+            w[o + "o.w"], w[o + "o.b"] = self._mat(sd[p + "attention.output.dense.weight"]), self._vec(sd[p + "attention.output.dense.bias"])
+            w[o + "ls1"], w[o + "ls2"] = self._vec(sd[p + "layer_scale1.lambda1"]), self._vec(sd[p + "layer_scale2.lambda1"])
+            w[o + "ln2.w"], w[o + "ln2.b"] = self._vec(sd[p + "norm2.weight"]), self._vec(sd[p + "norm2.bias"])
+            w[o + "fc1.w"], w[o + "fc1.b"] = self._mat(sd[p + "mlp.fc1.weight"]), self._vec(sd[p + "mlp.fc1.bias"])
+            w[o + "fc2.w"], w[o + "fc2.b"] = self._mat(sd[p + "mlp.fc2.weight"]), self._vec(sd[p + "mlp.fc2.bias"])
+        w["bridge0.w"], w["bridge0.b"] = self._mat(sd["img_txt_bridge.0.weight"]), self._vec(sd["img_txt_bridge.0.bias"])
+        w["bridge2.w"], w["bridge2.b"] = self._mat(sd["img_txt_bridge.2.weight"]), self._vec(sd["img_txt_bridge.2.bias"])
+        w["inproj.w"] = self._mat(sd["perceiver.input_proj.0.0.weight"].reshape(D, -1))
+        w["inproj.b"] = self._vec(sd["perceiver.input_proj.0.0.bias"])
+        w["inproj.ln.w"], w["inproj.ln.b"] = self._vec(sd["perceiver.input_proj.0.1.weight"]), self._vec(sd["perceiver.input_proj.0.1.bias"])
+        dt = "perceiver.ddetr_transformer."
+
+        def lin(dst, src):
+            w[dst + ".w"] = self._mat(sd[src + ".weight"])
+            if src + ".bias" in sd:
+                w[dst + ".b"] = self._vec(sd[src + ".bias"])
+
+        def ln(dst, src):
+            w[dst + ".w"], w[dst + ".b"] = self._vec(sd[src + ".weight"]), self._vec(sd[src + ".bias"])
+
+        def msda(dst, src):
+            w[dst + ".proj.w"] = self._mat(_cat(sd[src + ".sampling_offsets.weight"], sd[src + ".attention_weights.weight"]))
+            w[dst + ".proj.b"] = self._vec(_cat(sd[src + ".sampling_offsets.bias"], sd[src + ".attention_weights.bias"]))
+            lin(dst + ".value", src + ".value_proj")
+            lin(dst + ".out", src + ".output_proj")
+
+        for i in range(cfg.enc_layers):
+            p, o = f"{dt}encoder.layers.{i}.", f"enc.{i}."
+            msda(o + "sa", p + "self_attn"); ln(o + "ln1", p + "self_attn_layer_norm")
+            lin(o + "fc1", p + "fc1"); lin(o + "fc2", p + "fc2"); ln(o + "ln2", p + "final_layer_norm")
+        for i in range(cfg.dec_layers):
+            p, o = f"{dt}decoder.layers.{i}.", f"dec.{i}."
+            w[o + "qk.w"] = self._mat(_cat(sd[p + "self_attn.q_proj.weight"], sd[p + "self_attn.k_proj.weight"]))
+            w[o + "qk.b"] = self._vec(_cat(sd[p + "self_attn.q_proj.bias"], sd[p + "self_attn.k_proj.bias"]))
+            lin(o + "v", p + "self_attn.v_proj"); lin(o + "o", p + "self_attn.out_proj"); ln(o + "ln1", p + "self_attn_layer_norm")
+            msda(o + "ca", p + "encoder_attn"); ln(o + "ln2", p + "encoder_attn_layer_norm")
+            lin(o + "fc1", p + "fc1"); lin(o + "fc2", p + "fc2"); ln(o + "ln3", p + "final_layer_norm")
+        w["level_embed"] = sd[dt + "level_embed"].float()
+        w["query_tgt"] = self._mat(sd[dt + "query_position_embeddings.weight"])
+        lin("enc_output", dt + "enc_output"); ln("enc_output_norm", dt + "enc_output_norm")
+        lin("pos_trans", dt + "pos_trans"); ln("pos_trans_norm", dt + "pos_trans_norm")
+        lin("cls_enc", dt + "class_embed_enc")
+        L = cfg.dec_layers
+        lin("cls_coco", f"{dt}class_embed_coco.{L - 1}"); lin("cls_sa1b", f"{dt}class_embed_sa1b.{L - 1}")
+        for i in (L - 2, L - 1, L):
+            if i < 0:
+                continue
+            for j in range(3):
+                lin(f"bbox.{i}.{j}", f"{dt}bbox_embed.{i}.layers.{j}")
+        # region encoder
+        re_ = "region_encoder."
+        self.in_ld = H + 64
+        for l in range(3):
+            wi = torch.zeros(H, self.in_ld)
+            wi[:, :H + 2] = sd[f"{re_}mlvl_fuse.input_conv.{l}.weight"].reshape(H, H + 2).float()
+            w[f"inconv.{l}.w"], w[f"inconv.{l}.b"] = self._mat(wi), self._vec(sd[f"{re_}mlvl_fuse.input_conv.{l}.bias"])
+        for k in range(cfg.fuse_rounds):
+            cw = sd[f"{re_}mlvl_fuse.fuse_convs.{k}.conv.weight"]
+            w[f"fuse.{k}.w"] = self._mat(cw.permute(0, 2, 3, 1).reshape(H, 9 * H))
+            w[f"fuse.{k}.gn.w"], w[f"fuse.{k}.gn.b"] = self._vec(sd[f"{re_}mlvl_fuse.fuse_convs.{k}.gn.weight"]), self._vec(sd[f"{re_}mlvl_fuse.fuse_convs.{k}.gn.bias"])
+        w["pconv.w"] = self._mat(torch.cat([sd[f"{re_}roi_align.pconvs.{l}.weight"].permute(0, 2, 3, 1).reshape(H, 9 * H) for l in range(3)], 1))
+        w["pconv.b"] = self._vec(sum(sd[f"{re_}roi_align.pconvs.{l}.bias"].float() for l in range(3)))
+        # bf16-rounded values kept in fp32 for the K=4 linear
+        w["pos0.w"] = sd[re_ + "roi_align.pos_embedd.0.weight"].to(torch.bfloat16).float().to(self.dev).contiguous()
+        w["pos0.b"] = self._vec(sd[re_ + "roi_align.pos_embedd.0.bias"])
+        ln("pos2", re_ + "roi_align.pos_embedd.2"); lin("pos3", re_ + "roi_align.pos_embedd.3"); ln("pos5", re_ + "roi_align.pos_embedd.5")
+        lin("updims", re_ + "roi_align.updims")
+        fw = sd[re_ + "roi_align.flatten_linear.weight"]
+        n_mid, ro = fw.shape[0], cfg.roi_out
+        w["flatten.w"] = self._mat(fw.reshape(n_mid, H, ro * ro).permute(0, 2, 1).reshape(n_mid, ro * ro * H))  # (c,h,w) -> (h,w,c)
+        w["flatten.b"] = self._vec(sd[re_ + "roi_align.flatten_linear.bias"])
+        # LLaMA
+        w["embed"] = self._mat(sd["llm.model.embed_tokens.weight"])
+        w["new_embed"] = self._mat(sd["new_input_embs.weight"])
+        for i in range(cfg.llm_layers):
+            p, o = f"llm.model.layers.{i}.", f"llm.{i}."
+            w[o + "qkv.w"] = self._mat(_cat(*[sd[p + f"self_attn.{n}_proj.weight"] for n in ("q", "k", "v")]))
+            w[o + "o.w"] = self._mat(sd[p + "self_attn.o_proj.weight"])
+            g, u = sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"]
+            w[o + "gu.w"] = self._mat(torch.stack([g, u], 1).reshape(2 * g.shape[0], g.shape[1]))  # rows (gate_j, up_j) interleaved
+            w[o + "down.w"] = self._mat(sd[p + "mlp.down_proj.weight"])
+            w[o + "ln1"], w[o + "ln2"] = self._vec(sd[p + "input_layernorm.weight"]), self._vec(sd[p + "post_attention_layernorm.weight"])
+        w["llm.norm"] = self._vec(sd["llm.model.norm.weight"])
+        w["head.w"] = self._mat(_cat(sd["llm.lm_head.weight"], sd["extra_lm_head.weight"]))
+
+    def _interp_pos(self, pe: torch.Tensor) -> torch.Tensor:
+        """transformers-4.32 Dinov2Embeddings.interpolate_pos_encoding: bicubic with scale_factor (g+0.1)/G.
+        Input-independent -> computed once at load, on the host."""
+        cfg = self.cfg
+        Gp, g, dim = cfg.vit_pos_grid, cfg.grid, cfg.vit_hidden
+        if g == Gp:
+            return pe[0]
+        patch = pe[:, 1:].reshape(1, Gp, Gp, dim).permute(0, 3, 1, 2)
+        sf = (g + 0.1) / Gp
+        patch = F.interpolate(patch, scale_factor=(sf, sf), mode="bicubic", align_corners=False)
+        return torch.cat([pe[:, :1], patch.permute(0, 2, 3, 1).reshape(1, -1, dim)], 1)[0]
+
+    def _constants(self):
+        """Input-independent tensors of the proposer and region encoder (host-computed once)."""
+        cfg = self.cfg
+        g, D = cfg.grid, cfg.d_model
+        S = g * g
+        npf = D // 2
+        ones = torch.ones(1, g, g)
+        y_embed, x_embed = ones.cumsum(1, dtype=torch.float32), ones.cumsum(2, dtype=torch.float32)
+        y_embed = (y_embed - 0.5) / (y_embed[:, -1:, :] + 1e-6) * (2 * math.pi)
+        x_embed = (x_embed - 0.5) / (x_embed[:, :, -1:] + 1e-6) * (2 * math.pi)
+        dim_t = 10000 ** (2 * torch.div(torch.arange(npf, dtype=torch.float32), 2, rounding_mode="floor") / npf)
+        px, py = x_embed[:, :, :, None] / dim_t, y_embed[:, :, :, None] / dim_t
+        px = torch.stack((px[..., 0::2].sin(), px[..., 1::2].cos()), dim=4).flatten(3)
+        py = torch.stack((py[..., 0::2].sin(), py[..., 1::2].cos()), dim=4).flatten(3)
+        sine = torch.cat((py, px), dim=3).reshape(S, D)
+        self.enc_pos = (sine + self.w["level_embed"][0]).to(self.dev).to(torch.bfloat16).contiguous()
+        lin = torch.linspace(0.5, g - 0.5, g, dtype=torch.float32) / g
+        ry, rx = torch.meshgrid(lin, lin, indexing="ij")
+        self.enc_ref1 = torch.stack((rx.reshape(-1), ry.reshape(-1)), -1).to(self.dev).contiguous()  # [S,2]
+        ctr = (torch.arange(g, dtype=torch.float32) + 0.5) / g
+        gy, gx = torch.meshgrid(ctr, ctr, indexing="ij")
+        prop = torch.stack([gx.reshape(-1), gy.reshape(-1), torch.full((S,), 0.05), torch.full((S,), 0.05)], -1)
+        valid = ((prop > 0.01) & (prop < 0.99)).all(-1)
+        self.prop_logit = torch.log(prop / (1 - prop)).masked_fill(~valid[:, None], float("inf")).to(self.dev).contiguous()
+        self.prop_valid_all = bool(valid.all())
+        self.prop_valid = valid.to(torch.uint8).to(self.dev)
+        self.coord = {}
+        for s in (g * 4, g * 2, g):
+            self.coord[s] = torch.linspace(-1, 1, s).to(self.dev)
+        hd = cfg.head_dim
+        inv = 1.0 / (cfg.rope_theta ** (torch.arange(0, hd, 2).float() / hd))
+        fr = torch.outer(torch.arange(cfg.max_pos).float(), inv)
+        self.rope_cos, self.rope_sin = fr.cos().to(self.dev).contiguous(), fr.sin().to(self.dev).contiguous()
+
+    def _stage(self, name, t):
+        if self.keep_stages:
+            self.stages[name] = t
+
+    # ------------------------------------------------------------------------------------------ a1/a2 DINOv2
+    def vit(self, images: torch.Tensor) -> List[torch.Tensor]:
+        """$HF/models/dinov2/modeling_dinov2.py:57-149 (embeddings) and :348-387 x24 (layers); returns the hidden states
+        Groma reads: the last four layer outputs (groma.py:222-224,240-241,312)."""
+        cfg, w = self.cfg, self.w
+        B = images.shape[0]
+        H, nh = cfg.vit_hidden, cfg.vit_heads
+        hd = H // nh
+        NP = cfg.grid ** 2
+        S = NP + 1
+        patches = G.vit_patchify(images.to(self.dev, torch.float32), self.patch_ld)
+        emb = G.gemm(patches, w["vit.patch.w"], bias=w["vit.patch.b"])
+        x = G.vit_embed(emb, w["vit.cls"], w["vit.pos"], B, NP).reshape(B * S, H)
+        hs = []
+        keep_from = cfg.vit_layers - 4
+        for i in range(cfg.vit_layers):
+            o = f"vit.{i}."
+            y = G.layernorm(x, w[o + "ln1.w"], w[o + "ln1.b"], cfg.vit_ln_eps)
+            qkv = G.gemm(y, w[o + "qkv.w"], bias=w[o + "qkv.b"]).reshape(B, S, 3, nh, hd)
+            a = G.attention(qkv[:, :, 0], qkv[:, :, 1].permute(0, 2, 1, 3), qkv[:, :, 2].permute(0, 2, 1, 3),
+                            causal=False, scale=1.0 / math.sqrt(hd))
+            xn = torch.empty_like(x) if i >= keep_from else x   # keep the hidden states that are read later intact
+            G.gemm(a.reshape(B * S, H), w[o + "o.w"], bias=w[o + "o.b"], gamma=w[o + "ls1"], residual=x, out=xn)
+            x = xn
+            y = G.layernorm(x, w[o + "ln2.w"], w[o + "ln2.b"], cfg.vit_ln_eps)
+            h = G.gemm(y, w[o + "fc1.w"], bias=w[o + "fc1.b"], act=G.ACT_GELU)
+            G.gemm(h, w[o + "fc2.w"], bias=w[o + "fc2.b"], gamma=w[o + "ls2"], residual=x, out=x)
+            if i >= keep_from:
+                hs.append(x.reshape(B, S, H))
+        return hs
+
+    # ------------------------------------------------------------------------------------------ a3 image tokens
+    def image_tokens(self, last: torch.Tensor) -> torch.Tensor:
+        """groma.py:227-237 (2x2 token merge) + img_txt_bridge (groma.py:112-116,361)."""
+        B = last.shape[0]
+        f = G.space_to_depth(last, self.cfg.grid)
+        h = G.gemm(f.reshape(-1, f.shape[-1]), self.w["bridge0.w"], bias=self.w["bridge0.b"], act=G.ACT_GELU)
+        return G.gemm(h, self.w["bridge2.w"], bias=self.w["bridge2.b"]).reshape(B, -1, self.cfg.llm_hidden)
+
+    # ------------------------------------------------------------------------------------------ a4..a9 proposer
+    def _msda(self, pfx: str, query: torch.Tensor, value_src: torch.Tensor, ref: torch.Tensor, B: int, Q: int):
+        cfg, w = self.cfg, self.w
+        g = cfg.grid
+        proj = G.gemm(query, w[pfx + ".proj.w"], bias=w[pfx + ".proj.b"], out_f32=True)
+        value = G.gemm(value_src, w[pfx + ".value.w"], bias=w[pfx + ".value.b"])
+        return G.msda(value.reshape(B, g * g, cfg.ddetr_heads, 32), proj, ref, [(g, g)], cfg.ddetr_heads, cfg.n_points).reshape(B * Q, -1)
+
+    def proposer(self, hs: List[torch.Tensor], n_extra: int = 0):
+        """groma.py:240-249, ddetr.py:147-151, ddetr_transformer.py:484-609,668-728 (inference subset).
+        Returns fp32 (pred_cxcywh [B,N,4], pred_xyxy [B,N,4], scores [B,N]) with N = num_queries + n_extra slots."""
+        cfg, w = self.cfg, self.w
+        g, D, Qn = cfg.grid, cfg.d_model, cfg.num_queries
+        B, S = hs[0].shape[0], g * g
+        x = G.mean_tokens(hs[-4:], 1).reshape(B * S, -1)
+        src = G.gemm(x, w["inproj.w"], bias=w["inproj.b"])
+        x = G.layernorm(src, w["inproj.ln.w"], w["inproj.ln.b"], 1e-6)
+        self._stage("ddetr_src", x.reshape(B, S, D))
+        enc_ref = self.enc_ref1[None].expand(B, S, 2).contiguous()
+        for i in range(cfg.enc_layers):
+            o = f"enc.{i}."
+            q = G.add_bcast(x, self.enc_pos, S)
+            samp = self._msda(o + "sa", q, x, enc_ref, B, S)
+            h = G.gemm(samp, w[o + "sa.out.w"], bias=w[o + "sa.out.b"], residual=x)
+            x = G.layernorm(h, w[o + "ln1.w"], w[o + "ln1.b"], 1e-5)
+            t = G.gemm(x, w[o + "fc1.w"], bias=w[o + "fc1.b"], act=G.ACT_RELU)
+            h = G.gemm(t, w[o + "fc2.w"], bias=w[o + "fc2.b"], residual=x)
+            x = G.layernorm(h, w[o + "ln2.w"], w[o + "ln2.b"], 1e-5)
+        memory = x
+        self._stage("memory", memory.reshape(B, S, D))
+        oq = memory
+        if not self.prop_valid_all:
+            oq = G.mask_rows(memory.clone().reshape(B, S, D), self.prop_valid).reshape(B * S, D)
+        eo = G.layernorm(G.gemm(oq, w["enc_output.w"], bias=w["enc_output.b"]), w["enc_output_norm.w"], w["enc_output_norm.b"], 1e-5)
+        cls = G.gemm(eo, w["cls_enc.w"], bias=w["cls_enc.b"], out_f32=True).reshape(B, S)
+        L = cfg.dec_layers
+        t = G.gemm(eo, w[f"bbox.{L}.0.w"], bias=w[f"bbox.{L}.0.b"], act=G.ACT_RELU)
+        t = G.gemm(t, w[f"bbox.{L}.1.w"], bias=w[f"bbox.{L}.1.b"], act=G.ACT_RELU)
+        delta = G.gemm(t, w[f"bbox.{L}.2.w"], bias=w[f"bbox.{L}.2.b"], out_f32=True).reshape(B, S, 4)
+        topk = G.topk_desc(cls, Qn)
+        ref, pos512 = G.ddetr_select(delta, self.prop_logit, topk, D // 2)
+        self._stage("enc_cls", cls); self._stage("topk", topk); self._stage("ref_init", ref)
+        pt = G.layernorm(G.gemm(pos512.reshape(B * Qn, 2 * D), w["pos_trans.w"], bias=w["pos_trans.b"]),
+                         w["pos_trans_norm.w"], w["pos_trans_norm.b"], 1e-5)
+        query_pos = pt[:, :D].contiguous()
+        h = w["query_tgt"][None].expand(B, Qn, D).reshape(B * Qn, D).contiguous()
+        nH = cfg.ddetr_heads
+        hd = D // nH
+        keep = {}
+        for i in range(L):
+            o = f"dec.{i}."
+            qk_in = G.add(h, query_pos)
+            qk = G.gemm(qk_in, w[o + "qk.w"], bias=w[o + "qk.b"]).reshape(B, Qn, 2, nH, hd)
+            v = G.gemm(h, w[o + "v.w"], bias=w[o + "v.b"]).reshape(B, Qn, nH, hd)
+            a = G.attention(qk[:, :, 0], qk[:, :, 1].permute(0, 2, 1, 3), v.permute(0, 2, 1, 3), causal=False, scale=hd ** -0.5)
+            t = G.gemm(a.reshape(B * Qn, D), w[o + "o.w"], bias=w[o + "o.b"], residual=h)
+            h = G.layernorm(t, w[o + "ln1.w"], w[o + "ln1.b"], 1e-5)
+            qc = G.add(h, query_pos)
+            samp = self._msda(o + "ca", qc, memory, ref, B, Qn)
+            t = G.gemm(samp, w[o + "ca.out.w"], bias=w[o + "ca.out.b"], residual=h)
+            h = G.layernorm(t, w[o + "ln2.w"], w[o + "ln2.b"], 1e-5)
+            t = G.gemm(h, w[o + "fc1.w"], bias=w[o + "fc1.b"], act=G.ACT_RELU)
+            t = G.gemm(t, w[o + "fc2.w"], bias=w[o + "fc2.b"], residual=h)
+            h = G.layernorm(t, w[o + "ln3.w"], w[o + "ln3.b"], 1e-5)
+            keep[i] = h
+        self._stage("dec_last", keep[L - 1].reshape(B, Qn, D))
+
+        def bbox(i, hh):
+            t = G.gemm(hh, w[f"bbox.{i}.0.w"], bias=w[f"bbox.{i}.0.b"], act=G.ACT_RELU)
+            t = G.gemm(t, w[f"bbox.{i}.1.w"], bias=w[f"bbox.{i}.1.b"], act=G.ACT_RELU)
+            return G.gemm(t, w[f"bbox.{i}.2.w"], bias=w[f"bbox.{i}.2.b"], out_f32=True)
+
+        d5 = bbox(L - 1, keep[L - 1])
+        d4 = bbox(L - 2, keep[L - 2]) if L >= 2 else torch.zeros_like(d5)
+        coco = G.gemm(keep[L - 1], w["cls_coco.w"], bias=w["cls_coco.b"], out_f32=True)
+        sa1b = G.gemm(keep[L - 1], w["cls_sa1b.w"], bias=w["cls_sa1b.b"], out_f32=True)
+        N = Qn + n_extra
+        pc = torch.zeros((B, N, 4), dtype=torch.float32, device=self.dev)
+        px = torch.zeros((B, N, 4), dtype=torch.float32, device=self.dev)
+        sc = torch.zeros((B, N), dtype=torch.float32, device=self.dev)
+        G.ddetr_finalize(d4, d5, ref, coco, sa1b, pc, px, sc)
+        return pc, px, sc, {"coco": coco.reshape(B, Qn, 1), "sa1b": sa1b.reshape(B, Qn, 1)}
+
+    # ------------------------------------------------------------------------------------------ a10 region selection
+    def select_regions(self, pc, px, sc, refer_boxes: Optional[Sequence[torch.Tensor]], ground_boxes: Optional[Sequence[torch.Tensor]],
+                       nms_thres: float, score_thres: float, max_num: int) -> List[torch.Tensor]:
+        """groma.py:251-280.  NMS for the whole batch in one device kernel; the only host sync of the vision stage is the
+        read-back of keep indices.  torch.randperm stays on the global CPU RNG, one draw per image in image order (T6)."""
+        cfg = self.cfg
+        B, N = sc.shape
+        Qn = cfg.num_queries
+        counts = torch.full((B,), Qn, dtype=torch.int32)
+        if refer_boxes is not None or ground_boxes is not None:
+            for i in range(B):
+                extra = []
+                if refer_boxes is not None and len(refer_boxes[i]) > 0:
+                    extra.append((refer_boxes[i].to(self.dev, torch.float32), 1.0))
+                if ground_boxes is not None and len(ground_boxes[i]) > 0:
+                    extra.append((ground_boxes[i].to(self.dev, torch.float32), 0.2))
+                o = Qn
+                for bx, s in extra:
+                    n = bx.shape[0]
+                    pc[i, o:o + n] = bx
+                    px[i, o:o + n] = torch.cat([bx[:, :2] - 0.5 * bx[:, 2:], bx[:, :2] + 0.5 * bx[:, 2:]], -1)
+                    sc[i, o:o + n] = s
+                    o += n
+                counts[i] = o
+        keep, num, amax = G.nms_batched(px, sc, nms_thres, score_thres, max_num, counts=counts.to(self.dev))
+        keep_h, num_h, amax_h, pc_h = keep.cpu(), num.cpu(), amax.cpu(), pc.cpu()   # single sync point
+        self._stage("nms_keep", keep_h); self._stage("nms_num", num_h)
+        selected = []
+        for i in range(B):
+            n = int(num_h[i])
+            if n > 0:
+                bx = pc_h[i][keep_h[i, :n]]
+                bx = bx[torch.randperm(n)]
+            else:
+                mi = int(amax_h[i])
+                bx = pc_h[i][mi:mi + 1]
+            selected.append(bx)
+        return selected
+
+    # ------------------------------------------------------------------------------------------ a12/a13 region encoder
+    def region_encoder(self, hs: List[torch.Tensor], boxes: Sequence[torch.Tensor]) -> torch.Tensor:
+        """groma/model/roi_align.py:215-228 (upsample), :97-193 (MLVLFuseModule), :274-327 (MlvlRoIExtractor).
+        boxes: per-image [R_i,4] cxcywh (host or device).  Returns region features [sum R, llm_hidden] bf16."""
+        cfg, w = self.cfg, self.w
+        g, C = cfg.grid, cfg.vit_hidden
+        B = hs[0].shape[0]
+        sizes = [g * 4, g * 2, g]
+        xs = []
+        for l in range(3):
+            s = sizes[l]
+            up = G.upsample_coords(hs[len(hs) - 3 + l], 1, g, s, s, self.in_ld, self.coord[s], self.coord[s])
+            xs.append(G.gemm(up.reshape(-1, self.in_ld), w[f"inconv.{l}.w"], bias=w[f"inconv.{l}.b"]).reshape(B, s, s, C))
+        for k in range(cfg.fuse_rounds):
+            new = []
+            for l in range(3):
+                s = sizes[l]
+                xin = G.fuse_shuffle(xs[l], xs[min(l + 1, 2)], xs[max(l - 1, 0)])
+                y = G.conv3x3_flat(xin.reshape(-1, C), w[f"fuse.{k}.w"], B, s + 2, s + 2)
+                new.append(G.groupnorm_relu(y, w[f"fuse.{k}.gn.w"], w[f"fuse.{k}.gn.b"], cfg.gn_groups, 1e-5, B, out=y).reshape(B, s, s, C))
+            xs = new
+        if self.keep_stages:
+            self.stages["fused_maps"] = xs
+        allb = torch.cat([b.float() for b in boxes]).to(self.dev)
+        K = allb.shape[0]
+        if K == 0:
+            return torch.zeros((0, cfg.llm_hidden), dtype=torch.bfloat16, device=self.dev)
+        img_id = torch.cat([torch.full((len(b), 1), float(i)) for i, b in enumerate(boxes)]).to(self.dev)
+        rois = torch.cat([img_id, allb * float(cfg.image_size)], 1).contiguous()    # cxcywh*448 fed as xyxy (T1)
+        ro = cfg.roi_out
+        rp = ro + 2
+        rbuf = torch.empty((3, K, rp, rp, C), dtype=torch.bfloat16, device=self.dev)
+        for l in range(3):
+            G.roi_align(xs[l], rois, ro, (8, 4, 2)[l] / 14.0, cfg.roi_sampling, True, pad=True, out=rbuf[l])
+        fused = G.conv3x3_flat(rbuf.reshape(-1, C), w["pconv.w"], K, rp, rp, bias=w["pconv.b"], act=G.ACT_RELU)  # [K*ro*ro, C]
+        self._stage("roi_fused", fused.reshape(K, ro, ro, C))
+        flat_in = fused.reshape(K, ro * ro * C)
+        kt = flat_in.shape[1]
+        split = max(1, min(16, (148 * 2) // (((K + 127) // 128) * max(1, w["flatten.w"].shape[0] // 128))))
+        split = min(split, max(1, kt // 1024))
+        flat = G.gemm_splitk(flat_in, w["flatten.w"], split, bias=w["flatten.b"])
+        self._stage("region_flat", flat)
+        p = G.linear_smallk(allb, w["pos0.w"], w["pos0.b"], True)
+        p = G.layernorm(p, w["pos2.w"], w["pos2.b"], 1e-5)
+        p = G.gemm(p, w["pos3.w"], bias=w["pos3.b"], act=G.ACT_RELU)
+        p = G.layernorm(p, w["pos5.w"], w["pos5.b"], 1e-5)
+        z = G.add(flat, p)
+        return G.gemm(z, w["updims.w"], bias=w["updims.b"])
+
+    # ------------------------------------------------------------------------------------------ a15 embedding + splice
+    def embed(self, ids: torch.Tensor) -> torch.Tensor:
+        """groma.py:165-174: ids < vocab -> llm.embed_tokens, else new_input_embs[id - vocab]."""
+        flat = ids.reshape(-1).to(self.dev, torch.int64).contiguous()
+        return G.gather_rows(flat, self.w["embed"], self.w["new_embed"], self.cfg.vocab)
+
+    # ------------------------------------------------------------------------------------------ a16/a17 LLaMA
+    def alloc_kv(self, B: int, cap: int):
+        cfg = self.cfg
+        shape = (cfg.llm_layers, 2, B, cfg.llm_heads, cap, cfg.head_dim)
+        if self.kv is None or tuple(self.kv.shape) != shape:
+            self.kv = torch.zeros(shape, dtype=torch.bfloat16, device=self.dev)
+        self.kv_cap = cap
+
+    def llm_prefill(self, x: torch.Tensor, B: int, T: int, kv_len: torch.Tensor, last_only: bool = False) -> torch.Tensor:
+        """$HF/models/llama/modeling_llama.py LlamaModel forward (32 x LlamaDecoderLayer :292-340) + both heads
+        (groma.py:399-402).  x [B*T, hidden] bf16 (consumed), kv_len int32 [B] = valid (non-pad) length per row."""
+        cfg, w = self.cfg, self.w
+        nh, hd = cfg.llm_heads, cfg.head_dim
+        q = torch.empty((B * T, nh * hd), dtype=torch.bfloat16, device=self.dev)
+        for i in range(cfg.llm_layers):
+            o = f"llm.{i}."
+            y = G.rmsnorm(x, w[o + "ln1"], cfg.rms_eps)
+            qkv = G.gemm(y, w[o + "qkv.w"])
+            kc, vc = self.kv[i, 0], self.kv[i, 1]
+            G.rope_kv(qkv, q, kc, vc, self.rope_cos, self.rope_sin, B, T, nh, hd, 0)
+            a = G.attention(q.reshape(B, T, nh, hd), kc, vc, causal=True, scale=1.0 / math.sqrt(hd), kv_len=kv_len, sk=T)
+            G.gemm(a.reshape(B * T, nh * hd), w[o + "o.w"], residual=x, out=x)
+            y = G.rmsnorm(x, w[o + "ln2"], cfg.rms_eps)
+            gu = G.gemm(y, w[o + "gu.w"], act=G.ACT_SWIGLU)
+            G.gemm(gu, w[o + "down.w"], residual=x, out=x)
+        self.past = T
+        if last_only:
+            x = x.reshape(B, T, -1)[:, -1].contiguous()
+        h = G.rmsnorm(x, w["llm.norm"], cfg.rms_eps)
+        return G.gemm(h, w["head.w"], out_f32=True)
+
+    def _decode_buffers(self, B: int):
+        cfg = self.cfg
+        Hd, I, V = cfg.llm_hidden, cfg.llm_inter, cfg.vocab + cfg.num_new_token
+        key = (B,)
+        if getattr(self, "_dbuf_key", None) == key:
+            return self._dbuf
+        d = dict(
+            ids=torch.zeros((B,), dtype=torch.int64, device=self.dev),
+            x=torch.empty((B, Hd), dtype=torch.bfloat16, device=self.dev),
+            y=torch.empty((B, Hd), dtype=torch.bfloat16, device=self.dev),
+            qkv=torch.empty((B, 3 * Hd), dtype=torch.bfloat16, device=self.dev),
+            q=torch.empty((B, Hd), dtype=torch.bfloat16, device=self.dev),
+            a=torch.empty((B, 1, Hd), dtype=torch.bfloat16, device=self.dev),
+            gu=torch.empty((B, I), dtype=torch.bfloat16, device=self.dev),
+            ws=torch.empty((8 * max(3 * Hd, 2 * I, V) * B,), dtype=torch.float32, device=self.dev),
+            logits=torch.empty((B, V), dtype=torch.float32, device=self.dev),
+            pos=torch.zeros((1,), dtype=torch.int32, device=self.dev),
+            kv_len=torch.zeros((B,), dtype=torch.int32, device=self.dev),
+        )
+        self._dbuf, self._dbuf_key = d, key
+        return d
+
+    def _swap_gemm(self, x, wname, d, split, out, act=G.ACT_NONE, residual=None):
+        """out[B, N] = epilogue(x[B,K] @ W[N,K]^T) through the swap-AB tcgen05 path (weights stream once)."""
+        W = self.w[wname]
+        N, B = W.shape[0], x.shape[0]
+        ws = d["ws"][: split * N * B].view(split, N, B)
+        G.gemm_swap_ab(x, W, ws, split_k=split)
+        n_out = N // 2 if act == G.ACT_SWIGLU else N
+        G.splitk_reduce(ws, out, act=act, residual=residual, bias_along_m=True, ld_m=1, ld_n=n_out)
+        return out
+
+    def decode_step(self, B: int) -> torch.Tensor:
+        """One greedy decode step for the whole batch (groma.py:376-402 + HF greedy argmax): reads d['ids'], appends K/V at
+        *pos, attends to all kv_len[b] cached positions (all-ones mask, T7), writes next ids back to d['ids'].
+        Every shape-dependent scalar lives on the device, so the step is CUDA-graph capturable."""
+        cfg, w = self.cfg, self.w
+        d = self._decode_buffers(B)
+        nh, hd, Hd = cfg.llm_heads, cfg.head_dim, cfg.llm_hidden
+        G.gather_rows(d["ids"], w["embed"], w["new_embed"], cfg.vocab, out=d["x"])
+        x = d["x"]
+        for i in range(cfg.llm_layers):
+            o = f"llm.{i}."
+            G.rmsnorm(x, w[o + "ln1"], cfg.rms_eps, out=d["y"])
+            self._swap_gemm(d["y"], o + "qkv.w", d, 2, d["qkv"])
+            kc, vc = self.kv[i, 0], self.kv[i, 1]
+            G.rope_kv(d["qkv"], d["q"], kc, vc, self.rope_cos, self.rope_sin, B, 1, nh, hd, 0, pos_ptr=d["pos"])
+            G.attention(d["q"].reshape(B, 1, nh, hd), kc, vc, causal=False, scale=1.0 / math.sqrt(hd), kv_len=d["kv_len"],
+                        out=d["a"], sk=self.kv_cap)
+            self._swap_gemm(d["a"].reshape(B, Hd), o + "o.w", d, 4, x, residual=x)
+            G.rmsnorm(x, w[o + "ln2"], cfg.rms_eps, out=d["y"])
+            self._swap_gemm(d["y"], o + "gu.w", d, 1, d["gu"], act=G.ACT_SWIGLU)
+            self._swap_gemm(d["gu"], o + "down.w", d, 4, x, residual=x)
+        G.rmsnorm(x, w["llm.norm"], cfg.rms_eps, out=d["y"])
+        self._swap_gemm(d["y"], "head.w", d, 1, d["logits"])
+        G.argmax(d["logits"], out=d["ids"])
+        G.decode_advance(d["pos"], d["kv_len"])
+        return d["logits"]

@@ -392,9 +392,9 @@ def add_bcast(a: torch.Tensor, b: torch.Tensor, period: int, out: Optional[torch
 
 
 def rope_kv(qkv: torch.Tensor, q_out: torch.Tensor, cache_k: torch.Tensor, cache_v: torch.Tensor, cos_t: torch.Tensor,
-            sin_t: torch.Tensor, B: int, T: int, H: int, D: int, pos0: int):
+            sin_t: torch.Tensor, B: int, T: int, H: int, D: int, pos0: int, pos_ptr: Optional[torch.Tensor] = None):
     _chk(_L().groma_rope_kv(_p(qkv), _p(q_out), _p(cache_k), _p(cache_v), _p(cos_t), _p(sin_t), B, T, H, D, pos0,
-                            cache_k.shape[2], _stream()), "groma_rope_kv")
+                            _p(pos_ptr), cache_k.shape[2], _stream()), "groma_rope_kv")
 
 
 def argmax(logits: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -411,3 +411,17 @@ def to_bf16(x: torch.Tensor) -> torch.Tensor:
     out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     _chk(_L().groma_cast_f32_bf16(_p(x.contiguous()), _p(out), x.numel(), _stream()), "groma_cast_f32_bf16")
     return out
+
+
+def linear_smallk(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], relu: bool) -> torch.Tensor:
+    _f32(x, "x"); _f32(w, "w"); _f32(b, "b")
+    M, K = x.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+    _chk(_L().groma_linear_smallk(_p(x.contiguous()), _p(w), _p(b), _p(out), M, N, K, 1 if relu else 0, _stream()),
+         "groma_linear_smallk")
+    return out
+
+
+def decode_advance(pos: torch.Tensor, kv_len: torch.Tensor):
+    _chk(_L().groma_decode_advance(_p(pos), _p(kv_len), kv_len.numel(), _stream()), "groma_decode_advance")

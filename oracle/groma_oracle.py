@@ -39,6 +39,7 @@ class Oracle:
         self.prec = prec
         self.r = _bf if prec == "bf16" else (lambda x: x)
         # matrices (dim >= 2) are stored in bf16 on the device; vectors (bias / norm / LayerScale) stay fp32
+        # (v.float() is a no-op view for fp32 inputs, so the 7B-size fp32 oracle does not duplicate its 30 GB of weights)
         self.sd = {k: (self.r(v.float()) if v.dim() >= 2 else v.float()) for k, v in sd.items()}
         self.tok = None
         self.stages: Dict[str, torch.Tensor] = {}

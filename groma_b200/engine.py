@@ -171,7 +171,7 @@ class GromaEngine:
         px = torch.stack((px[..., 0::2].sin(), px[..., 1::2].cos()), dim=4).flatten(3)
         py = torch.stack((py[..., 0::2].sin(), py[..., 1::2].cos()), dim=4).flatten(3)
         sine = torch.cat((py, px), dim=3).reshape(S, D)
-        self.enc_pos = (sine + self.w["level_embed"][0]).to(self.dev).to(torch.bfloat16).contiguous()
+        self.enc_pos = (sine + self.w["level_embed"][0].cpu()).to(self.dev).to(torch.bfloat16).contiguous()
         lin = torch.linspace(0.5, g - 0.5, g, dtype=torch.float32) / g
         ry, rx = torch.meshgrid(lin, lin, indexing="ij")
         self.enc_ref1 = torch.stack((rx.reshape(-1), ry.reshape(-1)), -1).to(self.dev).contiguous()  # [S,2]

@@ -37,6 +37,7 @@ def parse_args():
     ap.add_argument("--new", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tiny", action="store_true", help="debug: miniature model")
+    ap.add_argument("--profile", action="store_true", help="print a per-stage CUDA-event breakdown of one step to stderr")
     return ap.parse_args()
 
 
@@ -98,12 +99,26 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------ reference arm (CPU)
+def usable_cores() -> int:
+    """Cores this process may actually use: affinity mask capped by the cgroup CPU quota (the GPU boxes expose 128 logical
+    CPUs under a 16-CPU quota; 128 threads there run ~20x slower than 16)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(p) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_reference(cfg, tok, T_text, n_new_full, sd_cpu, decode_steps=2):
     """The reference's CPU path = the fp32 oracle (oracle/groma_oracle.py; the reference itself cannot be imported in
     this image).  Bounded sample: ONE image -- vision + proposer + region encoder + prefill timed in full,
     `decode_steps` decode steps timed and extrapolated to the 128-token decode of the metric."""
     from oracle.groma_oracle import Oracle
-    torch.set_num_threads(os.cpu_count())
+    cores = usable_cores()
+    torch.set_num_threads(cores)
     o = Oracle(cfg, sd_cpu, "fp32")
     o.init_special_token_id(tok)
     images, ids = make_inputs(cfg, 1, T_text, 1234, tok)
@@ -117,7 +132,7 @@ def cpu_reference(cfg, tok, T_text, n_new_full, sd_cpu, decode_steps=2):
         nxt = lg[:, -1].argmax(-1)
     t2 = time.time()
     per_img = (t1 - t0) + (t2 - t1) / decode_steps * (n_new_full - 1)
-    return {"value": 1.0 / per_img, "unit": "images/sec", "cores": os.cpu_count(), "kind": "port",
+    return {"value": 1.0 / per_img, "unit": "images/sec", "cores": cores, "kind": "port",
             "sample": f"1 image, {T_text}-token prompt, R={len(out['selected_boxes'][0])}: vision+prefill {t1 - t0:.1f}s measured, "
                       f"{decode_steps} decode steps measured ({(t2 - t1) / decode_steps:.2f}s/step) extrapolated to {n_new_full - 1}",
             "prefill_s": t1 - t0, "decode_step_s": (t2 - t1) / decode_steps}
@@ -226,6 +241,14 @@ def main():
 
     for _ in range(max(args.warmup, 1)):
         step(True)
+    if args.profile and rank == 0:
+        model.profile = []
+        step(False)
+        torch.cuda.synchronize()
+        marks, model.profile = model.profile, None
+        for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+            print(f"[profile] {n1:>16s}: {e0.elapsed_time(e1):9.3f} ms", file=sys.stderr)
+        print(f"[profile] {'total':>16s}: {marks[0][1].elapsed_time(marks[-1][1]):9.3f} ms", file=sys.stderr)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()

@@ -164,6 +164,13 @@ class GromaModel(torch.nn.Module):
         self.box_idx_token_ids = None
         self.use_cuda_graph = True
         self._graph = None
+        self.profile = None   # set to a list to collect (stage name, cuda event) marks during generate()
+
+    def _mark(self, name: str):
+        if self.profile is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.profile.append((name, ev))
 
     # ------------------------------------------------------------------ loading (HF checkpoint layout)
     @classmethod
@@ -267,13 +274,16 @@ class GromaModel(torch.nn.Module):
     def _prefill_inputs(self, input_ids, images, refer_boxes, ground_boxes, labels=None, selected_override=None):
         eng, cfg = self.engine, self.config
         dev = eng.dev
+        self._mark("start")
         hs = eng.vit(images)
+        self._mark("vit")
         img_tok = eng.image_tokens(hs[-1])
         n_extra = 0
         B = images.shape[0]
         if refer_boxes is not None or ground_boxes is not None:
             n_extra = max((len(refer_boxes[i]) if refer_boxes is not None else 0) + (len(ground_boxes[i]) if ground_boxes is not None else 0) for i in range(B))
         pc, px, sc, det_logits = eng.proposer(hs, n_extra)
+        self._mark("proposer")
         if selected_override is not None:
             selected = [b.float().cpu() for b in selected_override]
         else:
@@ -285,7 +295,9 @@ class GromaModel(torch.nn.Module):
             input_ids.copy_(ids_h.to(input_ids.device))           # the reference edits the caller's tensor in place (T8)
             if labels is not None:
                 labels.copy_(labels_h.to(labels.device))
+        self._mark("select+match")
         region = eng.region_encoder(hs, selected)
+        self._mark("region_encoder")
         counts = [len(b) for b in selected]
         ids_new, labels_new = self._assemble(ids_h, labels_h, counts, img_tok.shape[1])
         Bn, T = ids_new.shape
@@ -371,7 +383,9 @@ class GromaModel(torch.nn.Module):
         B, T = ids_new.shape
         eng.alloc_kv(B, T + max_new_tokens)
         kv_len = mask.sum(1).to(torch.int32).to(dev)
+        self._mark("assemble+embed")
         logits = eng.llm_prefill(x, B, T, kv_len, last_only=True)          # [B, V] at the last (padded) position
+        self._mark("llm_prefill")
         d = eng._decode_buffers(B)
         G.argmax(logits, out=d["ids"])
         d["pos"].fill_(T)
@@ -396,6 +410,7 @@ class GromaModel(torch.nn.Module):
             if eos_token_id is not None and (s % check_every == 0):
                 if bool((out_tokens[:steps_done] == eos_token_id).any(0).all()):
                     break
+        self._mark("decode")
         eng.past = T + steps_done - 1
         new = out_tokens[:steps_done].t().contiguous()
         if eos_token_id is not None:

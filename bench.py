@@ -192,7 +192,7 @@ def main():
     realised = {}
 
     def step(host_inputs: bool):
-        torch.manual_seed(rank)   # randperm draws (groma.py:275) are per image, on the CPU generator
+        torch.manual_seed(0)      # same CPU generator state on every rank: randperm draws are replayed in global image order
         if host_inputs:
             img = images_h.cuda(non_blocking=True)
             ids = ids_h.cuda(non_blocking=True)
@@ -202,16 +202,9 @@ def main():
         seq = out.sequences
         boxes = out.hidden_states[0][-1]["pred_boxes"]
         if world > 1:
-            # the path's only exchange step: fixed-shape all-gather of ids + boxes
-            import torch.distributed as dist
-            R = torch.zeros((B, cfg.max_region_num, 4), device="cuda")
-            for i, b in enumerate(boxes):
-                R[i, :len(b)] = b
-            seq_all = torch.empty((world * B, seq.shape[1]), dtype=seq.dtype, device="cuda")
-            box_all = torch.empty((world * B, cfg.max_region_num, 4), device="cuda")
-            dist.all_gather_into_tensor(seq_all, seq.contiguous())
-            dist.all_gather_into_tensor(box_all, R)
-            seq = seq_all
+            # the path's only exchange step: fixed-shape all-gather of ids + boxes over NCCL
+            from groma_b200.dist import gather_outputs
+            seq, _, _ = gather_outputs(seq, boxes, cfg.max_region_num)
         if host_inputs:
             seq = seq.cpu()
         realised["R"] = [len(b) for b in boxes]

@@ -343,12 +343,14 @@ class GromaEngine:
         keep, num, amax = G.nms_batched(px, sc, nms_thres, score_thres, max_num, counts=counts.to(self.dev))
         keep_h, num_h, amax_h, pc_h = keep.cpu(), num.cpu(), amax.cpu(), pc.cpu()   # single sync point
         self._stage("nms_keep", keep_h); self._stage("nms_num", num_h)
+        from .dist import replayed_randperms
+        perms = replayed_randperms([int(n) for n in num_h])   # == [torch.randperm(n)] in a single process
         selected = []
         for i in range(B):
             n = int(num_h[i])
             if n > 0:
                 bx = pc_h[i][keep_h[i, :n]]
-                bx = bx[torch.randperm(n)]
+                bx = bx[perms[i]]
             else:
                 mi = int(amax_h[i])
                 bx = pc_h[i][mi:mi + 1]

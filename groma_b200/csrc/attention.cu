@@ -243,3 +243,123 @@ GROMA_API int32_t groma_attention(const void* q, int64_t q_bs, int64_t q_rs, con
     if (D == 32) return causal ? launch_attn<32, true>(p, B, st) : launch_attn<32, false>(p, B, st);
     return GROMA_ERR_UNSUPPORTED;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Decode attention (one query token per sequence): HBM-bound streaming of the K/V cache, no tensor cores.
+// One CTA per (head, batch row); 8 warps; a warp covers two keys per step (16 lanes x 16 bytes = one 256-byte K row per
+// half-warp), four steps in flight; online softmax per half-warp, merged through shared memory at the end.
+// Semantics = groma/model/groma.py:376-379 + eager LLaMA attention: every cached position < kv_len[b] is visible.
+namespace gb {
+
+constexpr int DEC_WARPS = 8, DEC_UNROLL = 4;
+
+template <int D>
+__global__ void __launch_bounds__(DEC_WARPS * 32) decode_attention_kernel(
+    const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc, const __nv_bfloat16* __restrict__ vc,
+    __nv_bfloat16* __restrict__ out, const int* __restrict__ kv_len, int H, long long cap, float scale_log2) {
+    static_assert(D == 128, "16 lanes x 8 dims");
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane >> 4, l = lane & 15;
+    const int n = kv_len[b];
+    const __nv_bfloat16* kb = kc + ((long long)b * H + h) * cap * D;
+    const __nv_bfloat16* vb = vc + ((long long)b * H + h) * cap * D;
+    float qf[8];
+    {
+        const uint4 qv = *reinterpret_cast<const uint4*>(q + ((long long)b * H + h) * D + l * 8);
+        const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&qv);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float2 f = __bfloat1622float2(q2[t]);
+            qf[2 * t] = f.x * scale_log2;
+            qf[2 * t + 1] = f.y * scale_log2;
+        }
+    }
+    float m = -INFINITY, lsum = 0.f, acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    constexpr int STEP = DEC_WARPS * 2;  // keys per block step
+    for (int base = warp * 2; base < n; base += STEP * DEC_UNROLL) {   // warp-uniform trip count (shuffles below)
+        const int j0 = base + grp;
+        uint4 kv4[DEC_UNROLL];
+        float s[DEC_UNROLL];
+#pragma unroll
+        for (int u = 0; u < DEC_UNROLL; ++u) {
+            const int j = j0 + u * STEP;
+            kv4[u] = (j < n) ? *reinterpret_cast<const uint4*>(kb + (long long)j * D + l * 8) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < DEC_UNROLL; ++u) {
+            const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kv4[u]);
+            float d = 0.f;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float2 f = __bfloat1622float2(k2[t]);
+                d += f.x * qf[2 * t] + f.y * qf[2 * t + 1];
+            }
+            d += __shfl_xor_sync(0xffffffffu, d, 8);
+            d += __shfl_xor_sync(0xffffffffu, d, 4);
+            d += __shfl_xor_sync(0xffffffffu, d, 2);
+            d += __shfl_xor_sync(0xffffffffu, d, 1);
+            s[u] = (j0 + u * STEP < n) ? d : -INFINITY;
+        }
+#pragma unroll
+        for (int u = 0; u < DEC_UNROLL; ++u) {
+            const int j = j0 + u * STEP;
+            kv4[u] = (j < n) ? *reinterpret_cast<const uint4*>(vb + (long long)j * D + l * 8) : make_uint4(0, 0, 0, 0);
+        }
+        float mn = m;
+#pragma unroll
+        for (int u = 0; u < DEC_UNROLL; ++u) mn = fmaxf(mn, s[u]);
+        const float mref = (mn == -INFINITY) ? 0.f : mn;   // half-warp without a valid key yet: everything stays 0
+        const float corr = exp2f(m - mref);               // m = -inf -> 0
+        m = mn;
+        lsum *= corr;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[t] *= corr;
+#pragma unroll
+        for (int u = 0; u < DEC_UNROLL; ++u) {
+            const float p = exp2f(s[u] - mref);
+            lsum += p;
+            const float pr = bf16_round(p);   // same rounding point as the tensor-core kernel's P operand
+            const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&kv4[u]);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float2 f = __bfloat1622float2(v2[t]);
+                acc[2 * t] += pr * f.x;
+                acc[2 * t + 1] += pr * f.y;
+            }
+        }
+    }
+    __shared__ float sm_m[DEC_WARPS * 2], sm_l[DEC_WARPS * 2], sm_acc[DEC_WARPS * 2][D];
+    const int slot = warp * 2 + grp;
+    if (l == 0) { sm_m[slot] = m; sm_l[slot] = lsum; }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) sm_acc[slot][l * 8 + t] = acc[t];
+    __syncthreads();
+    if (threadIdx.x < D) {
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < DEC_WARPS * 2; ++w) M = fmaxf(M, sm_m[w]);
+        float num = 0.f, den = 0.f;
+#pragma unroll
+        for (int w = 0; w < DEC_WARPS * 2; ++w) {
+            const float c = (sm_m[w] == -INFINITY) ? 0.f : exp2f(sm_m[w] - M);
+            num += c * sm_acc[w][threadIdx.x];
+            den += c * sm_l[w];
+        }
+        out[((long long)b * H + h) * D + threadIdx.x] = __float2bfloat16_rn(den > 0.f ? num / den : 0.f);
+    }
+}
+
+}  // namespace gb
+
+GROMA_API int32_t groma_decode_attention(const void* q, const void* cache_k, const void* cache_v, void* out,
+                                         const int32_t* kv_len, int32_t B, int32_t H, int32_t D, int64_t cap, float scale,
+                                         void* stream) {
+    if (!q || !cache_k || !cache_v || !out || !kv_len || B <= 0 || H <= 0) return GROMA_ERR_ARG;
+    if (D != 128) return GROMA_ERR_UNSUPPORTED;
+    gb::decode_attention_kernel<128><<<dim3(H, B), gb::DEC_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(cache_k),
+        reinterpret_cast<const __nv_bfloat16*>(cache_v), reinterpret_cast<__nv_bfloat16*>(out), kv_len, H, cap,
+        scale * 1.4426950408889634f);
+    return GROMA_LAUNCH_CHECK();
+}

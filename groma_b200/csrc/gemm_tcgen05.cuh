@@ -49,8 +49,22 @@ struct GemmCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * (32 * 80 + 32 * 8) /*epilogue staging*/;
 };
+
+// Grouped rasterisation: consecutive tiles walk GROUP_M m-blocks before advancing n, so the ~148 tiles in flight share
+// ~16 A row-blocks and ~9 B column-blocks -- both stay L2-resident instead of re-streaming B (180 MB for the 22016-wide
+// gate/up projection) once per 1.7 m-blocks as a plain n-fastest order did (measured 939 -> see profiles/).
+__device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, int& m_blk, int& n_blk) {
+    constexpr int GROUP_M = 16;
+    const int per_group = GROUP_M * n_tiles;
+    const int g = tile / per_group;
+    const int first_m = g * GROUP_M;
+    const int gsize = min(GROUP_M, m_tiles - first_m);
+    const int r = tile - g * per_group;
+    m_blk = first_m + r % gsize;
+    n_blk = r / gsize;
+}
 
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == ACT_GELU) return gelu_erf(v);
@@ -69,6 +83,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
     uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
     uint64_t* tempty_bar = tfull_bar + 2;       // [2]
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    constexpr int STG_WARP_BYTES = 32 * 80 + 32 * 8;  // 32 rows x (64 B + 16 B pad) + 32 output-row indices
+    uint8_t* stage_base = reinterpret_cast<uint8_t*>(tmem_holder + 4);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -112,7 +128,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
             for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
                 const int split = w % p.split_k;
                 const int tile = w / p.split_k;
-                const int n_blk = tile % n_tiles, m_blk = tile / n_tiles;
+                int m_blk, n_blk;
+                tile_coords(tile, m_tiles, n_tiles, m_blk, n_blk);
                 const int it0 = split * iters_per_split;
                 const int it1 = min(total_iters, it0 + iters_per_split);
                 for (int it = it0; it < it1; ++it) {
@@ -172,7 +189,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
         for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
             const int split = w % p.split_k;
             const int tile = w / p.split_k;
-            const int n_blk = tile % n_tiles, m_blk = tile / n_tiles;
+            int m_blk, n_blk;
+            tile_coords(tile, m_tiles, n_tiles, m_blk, n_blk);
             const int it0 = split * iters_per_split;
             const bool has_work = it0 < total_iters;  // an empty split contributes zeros
             mbar_wait(&tfull_bar[acc], acc_phase);
@@ -189,15 +207,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
                     out_row = (long long)img * (p.conv_hp - 2) * (p.conv_wp - 2) + (long long)(y - 1) * (p.conv_wp - 2) + (x - 1);
             }
             constexpr int CHUNK = (BN >= 32) ? 32 : 16;
+            // bf16 row-major outputs go through a warp-private shared-memory transpose so that global stores are
+            // sector-complete and coalesced (4 lanes x 16 B per 64-byte row segment) instead of 32 scattered 16-byte writes
+            const bool staged = !partial && !out_f32 && p.ld_n == 1 && (p.ld_m & 7) == 0 &&
+                                (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+            uint8_t* stg = stage_base + (warp - 2) * STG_WARP_BYTES;
+            long long* stg_rows = reinterpret_cast<long long*>(stg + 32 * 80);
+            if (staged) stg_rows[lane] = row_ok ? out_row : -1;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += CHUNK) {
                 uint32_t v[32];
                 const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + c0);
-                __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent stores below
+                __syncwarp();  // tcgen05.ld is .sync.aligned (and orders the staging buffer reuse)
                 if (CHUNK == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
                 tmem_ld_wait();
                 const int n0 = n_blk * BN + c0;
-                if (!row_ok || n0 >= p.N) continue;
+                const bool active = row_ok && n0 < p.N;
+                if (!staged && !active) continue;
                 if (!has_work) {
 #pragma unroll
                     for (int j = 0; j < CHUNK; ++j) v[j] = 0u;
@@ -213,83 +239,99 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
                     }
                     continue;
                 }
-                // ---- full epilogue
+                // ---- full epilogue: bias -> act -> gamma -> residual
+                const bool swiglu = p.act == ACT_SWIGLU;
+                const int out_cols = swiglu ? CHUNK / 2 : CHUNK;
+                const int no0 = swiglu ? (n0 >> 1) : n0;
+                const int NO = swiglu ? (p.N >> 1) : p.N;
                 float f[32];
-                const float bm = (bias_m && p.bias) ? p.bias[row] : 0.0f;
-                const float gm = (bias_m && p.gamma) ? p.gamma[row] : 1.0f;
+                if (active) {
+                    const float bm = (bias_m && p.bias) ? p.bias[row] : 0.0f;
+                    const float gm = (bias_m && p.gamma) ? p.gamma[row] : 1.0f;
 #pragma unroll
-                for (int j = 0; j < CHUNK; ++j) {
-                    float x = __uint_as_float(v[j]);
-                    const int n = n0 + j;
-                    if (p.bias) x += bias_m ? bm : (n < p.N ? p.bias[n] : 0.0f);
-                    f[j] = x;
-                }
-                if (p.act == ACT_SWIGLU) {
-                    // columns (2j, 2j+1) = (gate_j, up_j): out[:, n/2] = silu(gate) * up
-                    const int no0 = n0 >> 1;
-                    const int NO = p.N >> 1;
-                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ld_m + no0;
-                    float g[16];
+                    for (int j = 0; j < CHUNK; ++j) {
+                        float x = __uint_as_float(v[j]);
+                        const int n = n0 + j;
+                        if (p.bias) x += bias_m ? bm : (n < p.N ? p.bias[n] : 0.0f);
+                        f[j] = x;
+                    }
+                    if (swiglu) {
+                        // columns (2j, 2j+1) = (gate_j, up_j): out[:, n/2] = silu(gate) * up
 #pragma unroll
-                    for (int j = 0; j < CHUNK / 2; ++j) g[j] = silu(f[2 * j]) * f[2 * j + 1];
-                    if (p.ld_n == 1 && (p.ld_m & 7) == 0 && (no0 & 7) == 0 && no0 + CHUNK / 2 <= NO) {
-#pragma unroll
-                        for (int j = 0; j < CHUNK / 2; j += 8)
-                            *reinterpret_cast<uint4*>(dst + j) =
-                                make_uint4(pack_bf16x2(g[j], g[j + 1]), pack_bf16x2(g[j + 2], g[j + 3]),
-                                           pack_bf16x2(g[j + 4], g[j + 5]), pack_bf16x2(g[j + 6], g[j + 7]));
+                        for (int j = 0; j < CHUNK / 2; ++j) f[j] = silu(f[2 * j]) * f[2 * j + 1];
                     } else {
-                        _Pragma("unroll") for (int j = 0; j < CHUNK / 2; ++j) if (no0 + j < NO) dst[(long long)j * p.ld_n] = __float2bfloat16_rn(g[j]);
+#pragma unroll
+                        for (int j = 0; j < CHUNK; ++j) {
+                            float x = apply_act(f[j], p.act);
+                            const int n = n0 + j;
+                            if (p.gamma) x *= bias_m ? gm : (n < p.N ? p.gamma[n] : 1.0f);
+                            f[j] = x;
+                        }
+                        if (p.residual) {
+                            const __nv_bfloat16* r = p.residual + out_row * p.ld_m + (long long)n0 * p.ld_n;
+                            if (p.ld_n == 1 && (p.ld_m & 7) == 0 && n0 + CHUNK <= p.N) {
+#pragma unroll
+                                for (int j = 0; j < CHUNK; j += 8) {
+                                    const uint4 rv = *reinterpret_cast<const uint4*>(r + j);
+                                    const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                                    for (int t = 0; t < 4; ++t) {
+                                        const float2 rf = __bfloat1622float2(r2[t]);
+                                        f[j + 2 * t] += rf.x;
+                                        f[j + 2 * t + 1] += rf.y;
+                                    }
+                                }
+                            } else {
+                                _Pragma("unroll") for (int j = 0; j < CHUNK; ++j) if (n0 + j < p.N) f[j] += __bfloat162float(r[(long long)j * p.ld_n]);
+                            }
+                        }
+                    }
+                }
+                if (staged) {
+                    const int pitch = out_cols * 2 + 16;  // +16 B: conflict-free 16-byte row writes
+                    if (active) {
+                        uint4* srow = reinterpret_cast<uint4*>(stg + lane * pitch);
+#pragma unroll
+                        for (int j = 0; j < CHUNK; j += 8)
+                            if (j < out_cols)
+                                srow[j >> 3] = make_uint4(pack_bf16x2(f[j], f[j + 1]), pack_bf16x2(f[j + 2], f[j + 3]),
+                                                          pack_bf16x2(f[j + 4], f[j + 5]), pack_bf16x2(f[j + 6], f[j + 7]));
+                    }
+                    __syncwarp();
+                    const int lpr = out_cols >> 3;       // lanes per output row (16 B each)
+                    const int rpi = 32 / lpr;            // rows per store instruction
+                    __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out);
+                    for (int k = 0; k < lpr; ++k) {
+                        const int rr = k * rpi + lane / lpr, cc = lane % lpr;
+                        const long long orow = stg_rows[rr];
+                        const int col = no0 + cc * 8;
+                        if (orow >= 0 && col < NO) {
+                            const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * pitch + cc * 16);
+                            __nv_bfloat16* dst = ob + orow * p.ld_m + col;
+                            if (col + 8 <= NO) {
+                                *reinterpret_cast<uint4*>(dst) = val;
+                            } else {
+                                const __nv_bfloat16* hv = reinterpret_cast<const __nv_bfloat16*>(&val);
+                                for (int t = 0; t < 8 && col + t < NO; ++t) dst[t] = hv[t];
+                            }
+                        }
                     }
                     continue;
                 }
-#pragma unroll
-                for (int j = 0; j < CHUNK; ++j) {
-                    float x = apply_act(f[j], p.act);
-                    const int n = n0 + j;
-                    if (p.gamma) x *= bias_m ? gm : (n < p.N ? p.gamma[n] : 1.0f);
-                    f[j] = x;
-                }
-                const long long obase = out_row * p.ld_m + (long long)n0 * p.ld_n;
-                const bool vec_ok = p.ld_n == 1 && (p.ld_m & 7) == 0 && (n0 & 7) == 0 && n0 + CHUNK <= p.N;
-                if (p.residual) {
-                    const __nv_bfloat16* r = p.residual + obase;
-                    if (vec_ok) {
-#pragma unroll
-                        for (int j = 0; j < CHUNK; j += 8) {
-                            const uint4 rv = *reinterpret_cast<const uint4*>(r + j);
-                            const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                const float2 rf = __bfloat1622float2(r2[t]);
-                                f[j + 2 * t] += rf.x;
-                                f[j + 2 * t + 1] += rf.y;
-                            }
-                        }
-                    } else {
-                        _Pragma("unroll") for (int j = 0; j < CHUNK; ++j) if (n0 + j < p.N) f[j] += __bfloat162float(r[(long long)j * p.ld_n]);
-                    }
-                }
+                // ---- direct (unstaged) stores: fp32 outputs, strided / unaligned outputs
+                const long long obase = out_row * p.ld_m + (long long)no0 * p.ld_n;
                 if (out_f32) {
                     float* dst = reinterpret_cast<float*>(p.out) + obase;
-                    if (p.ld_n == 1 && (p.ld_m & 3) == 0 && (n0 & 3) == 0 && n0 + CHUNK <= p.N) {
+                    if (p.ld_n == 1 && (p.ld_m & 3) == 0 && (no0 & 3) == 0 && no0 + CHUNK <= NO && !swiglu) {
 #pragma unroll
                         for (int j = 0; j < CHUNK; j += 4)
                             *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
                     } else {
-                        _Pragma("unroll") for (int j = 0; j < CHUNK; ++j) if (n0 + j < p.N) dst[(long long)j * p.ld_n] = f[j];
+                        _Pragma("unroll") for (int j = 0; j < CHUNK; ++j) if (j < out_cols && no0 + j < NO) dst[(long long)j * p.ld_n] = f[j];
                     }
                 } else {
                     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + obase;
-                    if (vec_ok) {
-#pragma unroll
-                        for (int j = 0; j < CHUNK; j += 8)
-                            *reinterpret_cast<uint4*>(dst + j) =
-                                make_uint4(pack_bf16x2(f[j], f[j + 1]), pack_bf16x2(f[j + 2], f[j + 3]),
-                                           pack_bf16x2(f[j + 4], f[j + 5]), pack_bf16x2(f[j + 6], f[j + 7]));
-                    } else {
-                        _Pragma("unroll") for (int j = 0; j < CHUNK; ++j) if (n0 + j < p.N) dst[(long long)j * p.ld_n] = __float2bfloat16_rn(f[j]);
-                    }
+                    _Pragma("unroll") for (int j = 0; j < CHUNK; ++j) if (j < out_cols && no0 + j < NO) dst[(long long)j * p.ld_n] = __float2bfloat16_rn(f[j]);
                 }
             }
             // release this accumulator stage back to the MMA warp

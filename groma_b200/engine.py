@@ -457,13 +457,38 @@ class GromaEngine:
             q=torch.empty((B, Hd), dtype=torch.bfloat16, device=self.dev),
             a=torch.empty((B, 1, Hd), dtype=torch.bfloat16, device=self.dev),
             gu=torch.empty((B, I), dtype=torch.bfloat16, device=self.dev),
-            ws=torch.empty((8 * max(3 * Hd, 2 * I, V) * B,), dtype=torch.float32, device=self.dev),
+            ws=torch.empty((16 * max(3 * Hd, 2 * I, V) * B,), dtype=torch.float32, device=self.dev),
             logits=torch.empty((B, V), dtype=torch.float32, device=self.dev),
             pos=torch.zeros((1,), dtype=torch.int32, device=self.dev),
             kv_len=torch.zeros((B,), dtype=torch.int32, device=self.dev),
         )
         self._dbuf, self._dbuf_key = d, key
         return d
+
+    def _decode_splits(self):
+        """Split-K factors of the five decode GEMMs: (weight row-tiles of 128) x split should fill whole waves of the 148
+        SMs; e.g. gate/up has 172 tiles -> 1 split wastes 42% of the second wave, 6 splits give 1032 items = 6.97 waves."""
+        if getattr(self, "_splits", None) is None:
+            cfg = self.cfg
+
+            def pick(n_rows, k):
+                tiles = (n_rows + 127) // 128
+                kb = (k + 63) // 64
+                best, best_eff = 1, 0.0
+                for s in range(1, 17):
+                    if s > kb:
+                        break
+                    per = (kb + s - 1) // s
+                    s_eff = (kb + per - 1) // per          # splits that actually receive work
+                    items = tiles * s_eff
+                    waves = (items + 147) // 148
+                    eff = (tiles * kb) / (waves * 148 * per) - 0.004 * s   # small penalty: more fp32 partials to reduce
+                    if eff > best_eff:
+                        best, best_eff = s, eff
+                return best
+            Hd, I, V = cfg.llm_hidden, cfg.llm_inter, cfg.vocab + cfg.num_new_token
+            self._splits = dict(qkv=pick(3 * Hd, Hd), o=pick(Hd, Hd), gu=pick(2 * I, Hd), down=pick(Hd, I), head=pick(V, Hd))
+        return self._splits
 
     def _swap_gemm(self, x, wname, d, split, out, act=G.ACT_NONE, residual=None):
         """out[B, N] = epilogue(x[B,K] @ W[N,K]^T) through the swap-AB tcgen05 path (weights stream once)."""
@@ -490,20 +515,24 @@ class GromaEngine:
         nh, hd, Hd = cfg.llm_heads, cfg.head_dim, cfg.llm_hidden
         G.gather_rows(d["ids"], w["embed"], w["new_embed"], cfg.vocab, out=d["x"])
         x = d["x"]
+        sp = self._decode_splits()
         for i in range(cfg.llm_layers):
             o = f"llm.{i}."
             G.rmsnorm(x, w[o + "ln1"], cfg.rms_eps, out=d["y"])
-            self._swap_gemm(d["y"], o + "qkv.w", d, 2, d["qkv"])
+            self._swap_gemm(d["y"], o + "qkv.w", d, sp["qkv"], d["qkv"])
             kc, vc = self.kv[i, 0], self.kv[i, 1]
             G.rope_kv(d["qkv"], d["q"], kc, vc, self.rope_cos, self.rope_sin, B, 1, nh, hd, 0, pos_ptr=d["pos"])
-            G.attention(d["q"].reshape(B, 1, nh, hd), kc, vc, causal=False, scale=1.0 / math.sqrt(hd), kv_len=d["kv_len"],
-                        out=d["a"], sk=self.kv_cap)
-            self._swap_gemm(d["a"].reshape(B, Hd), o + "o.w", d, 4, x, residual=x)
+            if hd == 128:
+                G.decode_attention(d["q"], kc, vc, d["kv_len"], 1.0 / math.sqrt(hd), d["a"])
+            else:
+                G.attention(d["q"].reshape(B, 1, nh, hd), kc, vc, causal=False, scale=1.0 / math.sqrt(hd), kv_len=d["kv_len"],
+                            out=d["a"], sk=self.kv_cap)
+            self._swap_gemm(d["a"].reshape(B, Hd), o + "o.w", d, sp["o"], x, residual=x)
             G.rmsnorm(x, w[o + "ln2"], cfg.rms_eps, out=d["y"])
-            self._swap_gemm(d["y"], o + "gu.w", d, 1, d["gu"], act=G.ACT_SWIGLU)
-            self._swap_gemm(d["gu"], o + "down.w", d, 4, x, residual=x)
+            self._swap_gemm(d["y"], o + "gu.w", d, sp["gu"], d["gu"], act=G.ACT_SWIGLU)
+            self._swap_gemm(d["gu"], o + "down.w", d, sp["down"], x, residual=x)
         G.rmsnorm(x, w["llm.norm"], cfg.rms_eps, out=d["y"])
-        self._swap_gemm(d["y"], "head.w", d, 1, d["logits"])
+        self._swap_gemm(d["y"], "head.w", d, sp["head"], d["logits"])
         G.argmax(d["logits"], out=d["ids"])
         G.decode_advance(d["pos"], d["kv_len"])
         return d["logits"]

@@ -171,6 +171,17 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, causal: bool
     return out
 
 
+def decode_attention(q: torch.Tensor, cache_k: torch.Tensor, cache_v: torch.Tensor, kv_len: torch.Tensor, scale: float,
+                     out: torch.Tensor) -> torch.Tensor:
+    """q/out [B, H*D] bf16, cache_k/v [B, H, cap, D] contiguous, kv_len int32 [B] on device."""
+    _bf16(q, "q")
+    B, H, cap, D = cache_k.shape
+    assert cache_k.is_contiguous() and cache_v.is_contiguous() and q.is_contiguous() and out.is_contiguous()
+    rc = _L().groma_decode_attention(_p(q), _p(cache_k), _p(cache_v), _p(out), _p(kv_len), B, H, D, cap, float(scale), _stream())
+    _chk(rc, "groma_decode_attention")
+    return out
+
+
 # --------------------------------------------------------------------------------------------- norms
 def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float, *, residual: Optional[torch.Tensor] = None,
             h_out: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -69,6 +69,11 @@ int32_t groma_attention(const void* q, int64_t q_bs, int64_t q_rs, const void* k
                         int64_t o_rs, const int32_t* kv_len, int32_t B, int32_t H, int32_t Sq, int32_t Sk, int32_t D,
                         int32_t causal, int32_t q_pos0, float scale, void* stream);
 
+/* Single-query (decode) attention over the KV cache: every cached position < kv_len[b] is visible (the all-ones mask of
+ * groma/model/groma.py:376-379).  q, out [B, H*D]; cache_k/v [B, H, cap, D]; D = 128.  HBM-bound SIMT kernel. */
+int32_t groma_decode_attention(const void* q, const void* cache_k, const void* cache_v, void* out, const int32_t* kv_len,
+                               int32_t B, int32_t H, int32_t D, int64_t cap, float scale, void* stream);
+
 /* y = w * bf16(h * rsqrt(mean(h^2)+eps)), h = bf16(x + residual) (h_out optional).  LlamaRMSNorm,
  * $HF/models/llama/modeling_llama.py:53-70 (+ the residual add of :292-340). */
 int32_t groma_rmsnorm(const void* x, const void* residual, const float* w, void* y, void* h_out, int64_t rows,

@@ -246,30 +246,58 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
                 const int NO = swiglu ? (p.N >> 1) : p.N;
                 float f[32];
                 if (active) {
-                    const float bm = (bias_m && p.bias) ? p.bias[row] : 0.0f;
-                    const float gm = (bias_m && p.gamma) ? p.gamma[row] : 1.0f;
+                    // every runtime switch is hoisted out of the per-element loops (one predicated branch per chunk, not per
+                    // element: the first version spent its time in instruction-cache misses, see profiles/r01_gemm_epilogue.md)
+                    const bool full = n0 + CHUNK <= p.N;
 #pragma unroll
-                    for (int j = 0; j < CHUNK; ++j) {
-                        float x = __uint_as_float(v[j]);
-                        const int n = n0 + j;
-                        if (p.bias) x += bias_m ? bm : (n < p.N ? p.bias[n] : 0.0f);
-                        f[j] = x;
+                    for (int j = 0; j < CHUNK; ++j) f[j] = __uint_as_float(v[j]);
+                    if (p.bias) {
+                        if (bias_m) {
+                            const float bm = p.bias[row];
+#pragma unroll
+                            for (int j = 0; j < CHUNK; ++j) f[j] += bm;
+                        } else if (full) {
+#pragma unroll
+                            for (int j = 0; j < CHUNK; j += 4) {
+                                const float4 b4 = *reinterpret_cast<const float4*>(p.bias + n0 + j);
+                                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < CHUNK; ++j) if (n0 + j < p.N) f[j] += p.bias[n0 + j];
+                        }
                     }
                     if (swiglu) {
                         // columns (2j, 2j+1) = (gate_j, up_j): out[:, n/2] = silu(gate) * up
 #pragma unroll
                         for (int j = 0; j < CHUNK / 2; ++j) f[j] = silu(f[2 * j]) * f[2 * j + 1];
                     } else {
+                        if (p.act == ACT_GELU) {
 #pragma unroll
-                        for (int j = 0; j < CHUNK; ++j) {
-                            float x = apply_act(f[j], p.act);
-                            const int n = n0 + j;
-                            if (p.gamma) x *= bias_m ? gm : (n < p.N ? p.gamma[n] : 1.0f);
-                            f[j] = x;
+                            for (int j = 0; j < CHUNK; ++j) f[j] = gelu_erf(f[j]);
+                        } else if (p.act == ACT_RELU) {
+#pragma unroll
+                            for (int j = 0; j < CHUNK; ++j) f[j] = fmaxf(f[j], 0.0f);
+                        }
+                        if (p.gamma) {
+                            if (bias_m) {
+                                const float gm = p.gamma[row];
+#pragma unroll
+                                for (int j = 0; j < CHUNK; ++j) f[j] *= gm;
+                            } else if (full) {
+#pragma unroll
+                                for (int j = 0; j < CHUNK; j += 4) {
+                                    const float4 g4 = *reinterpret_cast<const float4*>(p.gamma + n0 + j);
+                                    f[j] *= g4.x; f[j + 1] *= g4.y; f[j + 2] *= g4.z; f[j + 3] *= g4.w;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < CHUNK; ++j) if (n0 + j < p.N) f[j] *= p.gamma[n0 + j];
+                            }
                         }
                         if (p.residual) {
                             const __nv_bfloat16* r = p.residual + out_row * p.ld_m + (long long)n0 * p.ld_n;
-                            if (p.ld_n == 1 && (p.ld_m & 7) == 0 && n0 + CHUNK <= p.N) {
+                            if (p.ld_n == 1 && (p.ld_m & 7) == 0 && full) {
 #pragma unroll
                                 for (int j = 0; j < CHUNK; j += 8) {
                                     const uint4 rv = *reinterpret_cast<const uint4*>(r + j);

@@ -119,8 +119,8 @@ GROMA_API int32_t groma_gemm_bf16(const void* A, int64_t a_rows, int64_t lda, co
                                    int64_t ldb, int32_t M, int32_t N, int32_t K, int32_t num_taps,
                                    const int32_t* a_row_off, void* out, int64_t ld_m, int64_t ld_n, int32_t flags,
                                    int32_t act, const float* bias, const float* gamma, const void* residual,
-                                   float* ws, int32_t split_k, int32_t conv_hp, int32_t conv_wp, int32_t block_n,
-                                   void* stream) {
+                                   float* ws, int32_t split_k, int32_t* tile_counters, int32_t conv_hp, int32_t conv_wp,
+                                   int32_t block_n, void* stream) {
     if (!A || !B || M <= 0 || N <= 0 || K <= 0) return GROMA_ERR_ARG;
     if (num_taps < 1 || num_taps > GEMM_MAX_TAPS) return GROMA_ERR_ARG;
     if ((lda & 7) || (ldb & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
@@ -129,6 +129,7 @@ GROMA_API int32_t groma_gemm_bf16(const void* A, int64_t a_rows, int64_t lda, co
     if (split_k > 1 && !(flags & GF_PARTIAL)) return GROMA_ERR_ARG;
     if ((flags & GF_PARTIAL) && !ws) return GROMA_ERR_ARG;
     if (!(flags & GF_PARTIAL) && !out) return GROMA_ERR_ARG;
+    if (tile_counters && (!(flags & GF_PARTIAL) || !out)) return GROMA_ERR_ARG;
     if (act == ACT_SWIGLU && (N & 1)) return GROMA_ERR_ARG;
     if (num_taps > 1 && (K % GEMM_BK) != 0) return GROMA_ERR_ARG;
 
@@ -155,7 +156,7 @@ GROMA_API int32_t groma_gemm_bf16(const void* A, int64_t a_rows, int64_t lda, co
     p.split_k = split_k; p.flags = flags; p.act = act;
     p.out = out; p.ld_m = ld_m; p.ld_n = ld_n;
     p.bias = bias; p.gamma = gamma; p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
-    p.ws = ws; p.conv_hp = conv_hp; p.conv_wp = conv_wp;
+    p.ws = ws; p.conv_hp = conv_hp; p.conv_wp = conv_wp; p.tile_counters = tile_counters;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     switch (bn) {
         case 16: return launch_gemm<16>(p, st);

@@ -40,6 +40,7 @@ struct GemmParams {
     const __nv_bfloat16* residual;  // same strides as out, or null
     float* ws;             // fp32 partials [split][M][N] when GF_PARTIAL
     int conv_hp, conv_wp;  // padded map dims for GF_CONV_ROWS
+    int* tile_counters;    // GF_PARTIAL + non-null: the CTA that completes a tile's last split reduces ws and runs the epilogue
 };
 
 template <int BN>
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
     constexpr int STG_WARP_BYTES = 32 * 80 + 32 * 8;  // 32 rows x (64 B + 16 B pad) + 32 output-row indices
     uint8_t* stage_base = reinterpret_cast<uint8_t*>(tmem_holder + 4);
+    volatile int* finish_flag = reinterpret_cast<volatile int*>(tmem_holder + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -361,6 +363,74 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
                     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + obase;
                     _Pragma("unroll") for (int j = 0; j < CHUNK; ++j) if (j < out_cols && no0 + j < NO) dst[(long long)j * p.ld_n] = __float2bfloat16_rn(f[j]);
                 }
+            }
+            // ---- fused split-K finish: the last CTA to deliver a partial of this tile sums all splits (fixed order, so the
+            //      result is deterministic) and runs the epilogue -- no separate reduce launch on the decode path
+            if (partial && p.tile_counters != nullptr) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);   // TMEM no longer needed: let the MMA warp run ahead
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (warp == 2 && lane == 0) {
+                    const int old = atomicAdd(p.tile_counters + tile, 1);
+                    const int last = (old == p.split_k - 1) ? 1 : 0;
+                    if (last) p.tile_counters[tile] = 0;        // re-arm for the next launch / graph replay
+                    *finish_flag = last;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (*finish_flag) {
+                    __threadfence();
+                    const bool swiglu_m = (p.act == ACT_SWIGLU);   // pairs along M: rows (2j, 2j+1) = (gate_j, up_j)
+                    const float bm = (row_ok && p.bias && bias_m) ? p.bias[row] : 0.0f;
+                    const float gm = (row_ok && p.gamma && bias_m) ? p.gamma[row] : 1.0f;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < BN; c0 += 16) {
+                        const int n0 = n_blk * BN + c0;
+                        if (n0 >= p.N) break;
+                        float a16[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) a16[j] = 0.0f;
+                        if (row_ok) {
+                            for (int sp = 0; sp < p.split_k; ++sp) {
+                                const float* src = p.ws + ((long long)sp * p.M + out_row) * p.N + n0;
+                                if ((p.N & 3) == 0 && n0 + 16 <= p.N) {
+#pragma unroll
+                                    for (int j = 0; j < 16; j += 4) {
+                                        const float4 t4 = __ldcg(reinterpret_cast<const float4*>(src + j));
+                                        a16[j] += t4.x; a16[j + 1] += t4.y; a16[j + 2] += t4.z; a16[j + 3] += t4.w;
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) if (n0 + j < p.N) a16[j] += __ldcg(src + j);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int n = n0 + j;
+                            float x = a16[j];
+                            if (p.bias) x += bias_m ? bm : (n < p.N ? p.bias[n] : 0.0f);
+                            if (swiglu_m) {
+                                const float other = __shfl_xor_sync(0xffffffffu, x, 1);
+                                if (row_ok && !(row & 1) && n < p.N)
+                                    reinterpret_cast<__nv_bfloat16*>(p.out)[(out_row >> 1) * p.ld_m + (long long)n * p.ld_n] =
+                                        __float2bfloat16_rn(silu(x) * other);
+                                continue;
+                            }
+                            x = apply_act(x, p.act);
+                            if (p.gamma) x *= bias_m ? gm : (n < p.N ? p.gamma[n] : 1.0f);
+                            if (row_ok && n < p.N) {
+                                const long long o = out_row * p.ld_m + (long long)n * p.ld_n;
+                                if (p.residual) x += __bfloat162float(p.residual[o]);
+                                if (out_f32) reinterpret_cast<float*>(p.out)[o] = x;
+                                else reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16_rn(x);
+                            }
+                        }
+                    }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                continue;
             }
             // release this accumulator stage back to the MMA warp
             tc_fence_before();

@@ -460,6 +460,7 @@ class GromaEngine:
             ws=torch.empty((16 * max(3 * Hd, 2 * I, V) * B,), dtype=torch.float32, device=self.dev),
             logits=torch.empty((B, V), dtype=torch.float32, device=self.dev),
             pos=torch.zeros((1,), dtype=torch.int32, device=self.dev),
+            cnt=torch.zeros((1024,), dtype=torch.int32, device=self.dev),   # split-K tile counters (self re-arming)
             kv_len=torch.zeros((B,), dtype=torch.int32, device=self.dev),
         )
         self._dbuf, self._dbuf_key = d, key
@@ -498,12 +499,10 @@ class GromaEngine:
         if self.timing_hook is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        G.gemm_swap_ab(x, W, ws, split_k=split)
+        G.gemm_swap_ab_fused(x, W, ws, d["cnt"], split, out, act=act, residual=residual)
         if self.timing_hook is not None:
             ev1.record()
-            self.timing_hook.append((ev0, ev1, W.numel() * 2 + x.numel() * 2 + ws.numel() * 4))
-        n_out = N // 2 if act == G.ACT_SWIGLU else N
-        G.splitk_reduce(ws, out, act=act, residual=residual, bias_along_m=True, ld_m=1, ld_n=n_out)
+            self.timing_hook.append((ev0, ev1, W.numel() * 2 + x.numel() * 2 + out.numel() * out.element_size()))
         return out
 
     def decode_step(self, B: int) -> torch.Tensor:

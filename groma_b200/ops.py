@@ -70,7 +70,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         _bf16(residual, "residual")
         assert residual.stride() == out.stride()
     rc = _L().groma_gemm_bf16(_p(a), a.shape[0], a.stride(0), _p(w), w.shape[0], w.stride(0), M, N, K, 1, None,
-                              _p(out), out.stride(0), 1, flags, act, _p(bias), _p(gamma), _p(residual), None, 1, 0, 0,
+                              _p(out), out.stride(0), 1, flags, act, _p(bias), _p(gamma), _p(residual), None, 1, None, 0, 0,
                               block_n, _stream())
     _chk(rc, "groma_gemm_bf16")
     return out
@@ -86,7 +86,7 @@ def gemm_splitk(a: torch.Tensor, w: torch.Tensor, split_k: int, *, bias=None, ac
     if ws is None:
         ws = torch.empty((split_k, M, N), dtype=torch.float32, device=a.device)
     rc = _L().groma_gemm_bf16(_p(a), M, a.stride(0), _p(w), N, w.stride(0), M, N, K, 1, None, None, 0, 0, GF_PARTIAL,
-                              ACT_NONE, None, None, None, _p(ws), split_k, 0, 0, block_n, _stream())
+                              ACT_NONE, None, None, None, _p(ws), split_k, None, 0, 0, block_n, _stream())
     _chk(rc, "groma_gemm_bf16(split-k)")
     n_out = N // 2 if act == ACT_SWIGLU else N
     if out is None:
@@ -105,9 +105,26 @@ def gemm_swap_ab(x: torch.Tensor, w: torch.Tensor, ws: torch.Tensor, split_k: in
     M, K = x.shape
     N = w.shape[0]
     rc = _L().groma_gemm_bf16(_p(w), N, w.stride(0), _p(x), M, x.stride(0), N, M, K, 1, None, None, 0, 0, GF_PARTIAL,
-                              ACT_NONE, None, None, None, _p(ws), split_k, 0, 0, block_n, _stream())
+                              ACT_NONE, None, None, None, _p(ws), split_k, None, 0, 0, block_n, _stream())
     _chk(rc, "groma_gemm_bf16(swap-ab)")
     return ws
+
+
+def gemm_swap_ab_fused(x: torch.Tensor, w: torch.Tensor, ws: torch.Tensor, counters: torch.Tensor, split_k: int,
+                       out: torch.Tensor, *, act: int = ACT_NONE, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Decode GEMM in one launch: out[M, N(/2)] = epilogue(x[M,K] @ w[N,K]^T).  Weights are the 128-row MMA operand
+    (swap-AB), K is split over CTAs, and the CTA that finishes a weight tile last reduces the fp32 partials and writes the
+    bf16 / fp32 rows of `out` (transposed store, optional residual add, optional SwiGLU over interleaved weight rows)."""
+    _bf16(x, "x"); _bf16(w, "w")
+    M, K = x.shape
+    N = w.shape[0]
+    n_out = N // 2 if act == ACT_SWIGLU else N
+    assert out.shape == (M, n_out) and out.is_contiguous() and counters.dtype == torch.int32
+    flags = GF_PARTIAL | GF_BIAS_ALONG_M | (GF_OUT_F32 if out.dtype == torch.float32 else 0)
+    rc = _L().groma_gemm_bf16(_p(w), N, w.stride(0), _p(x), M, x.stride(0), N, M, K, 1, None, _p(out), 1, n_out, flags, act,
+                              None, None, _p(residual), _p(ws), split_k, _p(counters), 0, 0, 0, _stream())
+    _chk(rc, "groma_gemm_bf16(swap-ab fused)")
+    return out
 
 
 def conv3x3_flat(x_pad: torch.Tensor, w_taps: torch.Tensor, n_img: int, hp: int, wp: int, *, bias=None, act=ACT_NONE,
@@ -135,7 +152,7 @@ def conv3x3_flat(x_pad: torch.Tensor, w_taps: torch.Tensor, n_img: int, hp: int,
     flags = GF_CONV_ROWS | (GF_CONV_COMPACT if compact else 0)
     rc = _L().groma_gemm_bf16(_p(x_pad), x_pad.shape[0], x_pad.stride(0), _p(w_taps), Cout, w_taps.stride(0), rows,
                               Cout, C, L * 9, _i32_array(offs), _p(out), out.stride(0), 1, flags, act, _p(bias), None,
-                              None, None, 1, hp, wp, block_n, _stream())
+                              None, None, 1, None, hp, wp, block_n, _stream())
     _chk(rc, "groma_gemm_bf16(conv3x3)")
     return out
 

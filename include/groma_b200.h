@@ -47,12 +47,15 @@ extern "C" {
  * residual bf16 with the strides of out.  GROMA_GF_PARTIAL: raw fp32 accumulators to ws[split][M][N] (split_k >= 1).
  * GROMA_GF_CONV_ROWS: rows are pixels of [img][conv_hp][conv_wp] maps, border rows are not written;
  * with GROMA_GF_CONV_COMPACT the row index is that of the un-padded [img][hp-2][wp-2] layout.
+ * tile_counters (optional, with GROMA_GF_PARTIAL): zero-initialised int32[m_tiles*n_tiles]; the CTA that delivers the last
+ * split of a tile sums ws over the splits in fixed order and applies the epilogue to `out` itself (no groma_splitk_reduce
+ * launch); with GROMA_ACT_SWIGLU + GROMA_GF_BIAS_ALONG_M the (gate, up) pairs are adjacent ROWS (swap-AB decode layout).
  * block_n: 0 = auto, else 16/32/64/128/256. */
 int32_t groma_gemm_bf16(const void* A, int64_t a_rows, int64_t lda, const void* B, int64_t b_rows, int64_t ldb,
                         int32_t M, int32_t N, int32_t K, int32_t num_taps, const int32_t* a_row_off /*host*/,
                         void* out, int64_t ld_m, int64_t ld_n, int32_t flags, int32_t act, const float* bias,
-                        const float* gamma, const void* residual, float* ws, int32_t split_k, int32_t conv_hp,
-                        int32_t conv_wp, int32_t block_n, void* stream);
+                        const float* gamma, const void* residual, float* ws, int32_t split_k,
+                        int32_t* tile_counters, int32_t conv_hp, int32_t conv_wp, int32_t block_n, void* stream);
 
 /* out = epilogue(sum_s ws[s][M][N]) -- the deferred epilogue of a GROMA_GF_PARTIAL GEMM (same chain as above). */
 int32_t groma_splitk_reduce(const float* ws, int32_t splits, int32_t M, int32_t N, int32_t act, int32_t flags,

@@ -58,3 +58,30 @@ def test_swap_ab_reduce_epilogues(G):
         o3 = torch.empty(B, N, dtype=torch.float32, device="cuda")
         G.splitk_reduce(ws, o3, bias_along_m=True, ld_m=1, ld_n=N)
         assert ((o3.cpu() - ref).abs().max() / ref.abs().max()) < 2e-5
+
+
+def test_swap_ab_fused_finish(G):
+    """One-launch decode GEMM: last-arriving CTA reduces the split-K partials and runs the epilogue; counters re-arm."""
+    cnt = torch.zeros(1024, dtype=torch.int32, device="cuda")
+    for (B, K, N) in [(16, 512, 768), (3, 1024, 4096), (16, 4096, 1000)]:
+        x = rnd(B, K, seed=7).bfloat16(); w = rnd(N, K, seed=8, scale=0.05).bfloat16(); res = rnd(B, N, seed=9).bfloat16()
+        ref = x.float() @ w.float().t()
+        for split in (1, 3, 8):
+            ws = torch.empty(split * N * B, dtype=torch.float32, device="cuda").view(split, N, B)
+            for rep in range(2):   # second pass checks the counters were reset by the finishing CTAs
+                out = torch.empty(B, N, dtype=torch.bfloat16, device="cuda")
+                G.gemm_swap_ab_fused(x.cuda(), w.cuda(), ws, cnt, split, out, residual=res.cuda())
+                want = ref + res.float()
+                assert ((out.float().cpu() - want).abs().max() / want.abs().max()) < 6e-3, (B, K, N, split, rep)
+            assert int(cnt.abs().sum()) == 0
+            o2 = torch.empty(B, N // 2, dtype=torch.bfloat16, device="cuda")
+            G.gemm_swap_ab_fused(x.cuda(), w.cuda(), ws, cnt, split, o2, act=G.ACT_SWIGLU)
+            want2 = F.silu(ref[:, 0::2]) * ref[:, 1::2]
+            assert ((o2.float().cpu() - want2).abs().max() / want2.abs().max()) < 6e-3
+            o3 = torch.empty(B, N, dtype=torch.float32, device="cuda")
+            G.gemm_swap_ab_fused(x.cuda(), w.cuda(), ws, cnt, split, o3)
+            assert ((o3.cpu() - ref).abs().max() / ref.abs().max()) < 2e-5
+            # in-place residual (out aliases residual), as the decode loop uses it
+            r = res.clone().cuda()
+            G.gemm_swap_ab_fused(x.cuda(), w.cuda(), ws, cnt, split, r, residual=r)
+            assert ((r.float().cpu() - (ref + res.float())).abs().max() / (ref + res.float()).abs().max()) < 6e-3

@@ -130,7 +130,8 @@ GROMA_API int32_t groma_gemm_bf16(const void* A, int64_t a_rows, int64_t lda, co
     if ((flags & GF_PARTIAL) && !ws) return GROMA_ERR_ARG;
     if (!(flags & GF_PARTIAL) && !out) return GROMA_ERR_ARG;
     if (tile_counters && (!(flags & GF_PARTIAL) || !out)) return GROMA_ERR_ARG;
-    if (act == ACT_SWIGLU && (N & 1)) return GROMA_ERR_ARG;
+    if (act == ACT_SWIGLU && !(flags & GF_BIAS_ALONG_M) && (N & 1)) return GROMA_ERR_ARG;
+    if (act == ACT_SWIGLU && (flags & GF_BIAS_ALONG_M) && (M & 1)) return GROMA_ERR_ARG;
     if (num_taps > 1 && (K % GEMM_BK) != 0) return GROMA_ERR_ARG;
 
     int bn = block_n;

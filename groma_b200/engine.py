@@ -34,6 +34,7 @@ class GromaEngine:
         self.kv = None
         self.stages: Dict[str, torch.Tensor] = {}
         self.keep_stages = False
+        self.fused_splitk = False
         self.timing_hook = None   # bench.py: list collecting (start_event, end_event, algorithmic_bytes) per swap-AB GEMM
 
     # ------------------------------------------------------------------------------------------ weights
@@ -499,10 +500,18 @@ class GromaEngine:
         if self.timing_hook is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        G.gemm_swap_ab_fused(x, W, ws, d["cnt"], split, out, act=act, residual=residual)
+        if self.fused_splitk:
+            # one launch: the CTA finishing a tile last reduces the partials (measured SLOWER at decode tile sizes: the
+            # per-tile release fence + atomic sit on the epilogue's critical path; kept for larger-K uses, off by default)
+            G.gemm_swap_ab_fused(x, W, ws, d["cnt"], split, out, act=act, residual=residual)
+        else:
+            G.gemm_swap_ab(x, W, ws, split_k=split)
         if self.timing_hook is not None:
             ev1.record()
-            self.timing_hook.append((ev0, ev1, W.numel() * 2 + x.numel() * 2 + out.numel() * out.element_size()))
+            self.timing_hook.append((ev0, ev1, W.numel() * 2 + x.numel() * 2 + ws.numel() * 4))
+        if not self.fused_splitk:
+            n_out = N // 2 if act == G.ACT_SWIGLU else N
+            G.splitk_reduce(ws, out, act=act, residual=residual, bias_along_m=True, ld_m=1, ld_n=n_out)
         return out
 
     def decode_step(self, B: int) -> torch.Tensor:

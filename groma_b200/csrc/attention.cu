@@ -251,7 +251,14 @@ GROMA_API int32_t groma_attention(const void* q, int64_t q_bs, int64_t q_rs, con
 // Semantics = groma/model/groma.py:376-379 + eager LLaMA attention: every cached position < kv_len[b] is visible.
 namespace gb {
 
-constexpr int DEC_WARPS = 8, DEC_UNROLL = 4;
+constexpr int DEC_WARPS = 4, DEC_UNROLL = 4;   // 4 warps x 94 regs -> 5 CTAs/SM: all B*H CTAs resident in one wave
+
+// streaming 16-byte load that does not allocate in L1 (the KV cache is read once per step)
+__device__ __forceinline__ uint4 ld_nc_u4(const __nv_bfloat16* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
 
 template <int D>
 __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attention_kernel(
@@ -277,18 +284,34 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attention_kernel(
     }
     float m = -INFINITY, lsum = 0.f, acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     constexpr int STEP = DEC_WARPS * 2;  // keys per block step
+    // software pipeline: the K rows of the next step and the V rows of this step are requested before this step's
+    // arithmetic, so 8 x 16-byte loads per lane are in flight (HBM-bound: ~115 KB outstanding per SM)
+    uint4 kcur[DEC_UNROLL];
+    {
+        const int j0 = warp * 2 + grp;
+#pragma unroll
+        for (int u = 0; u < DEC_UNROLL; ++u) {
+            const int j = j0 + u * STEP;
+            kcur[u] = (j < n) ? ld_nc_u4(kb + (long long)j * D + l * 8) : make_uint4(0, 0, 0, 0);
+        }
+    }
     for (int base = warp * 2; base < n; base += STEP * DEC_UNROLL) {   // warp-uniform trip count (shuffles below)
         const int j0 = base + grp;
-        uint4 kv4[DEC_UNROLL];
+        uint4 vv[DEC_UNROLL], knext[DEC_UNROLL];
         float s[DEC_UNROLL];
 #pragma unroll
         for (int u = 0; u < DEC_UNROLL; ++u) {
             const int j = j0 + u * STEP;
-            kv4[u] = (j < n) ? *reinterpret_cast<const uint4*>(kb + (long long)j * D + l * 8) : make_uint4(0, 0, 0, 0);
+            vv[u] = (j < n) ? ld_nc_u4(vb + (long long)j * D + l * 8) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int u = 0; u < DEC_UNROLL; ++u) {
-            const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kv4[u]);
+            const int j = j0 + (u + DEC_UNROLL) * STEP;
+            knext[u] = (j < n) ? ld_nc_u4(kb + (long long)j * D + l * 8) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < DEC_UNROLL; ++u) {
+            const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kcur[u]);
             float d = 0.f;
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
@@ -300,11 +323,6 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attention_kernel(
             d += __shfl_xor_sync(0xffffffffu, d, 2);
             d += __shfl_xor_sync(0xffffffffu, d, 1);
             s[u] = (j0 + u * STEP < n) ? d : -INFINITY;
-        }
-#pragma unroll
-        for (int u = 0; u < DEC_UNROLL; ++u) {
-            const int j = j0 + u * STEP;
-            kv4[u] = (j < n) ? *reinterpret_cast<const uint4*>(vb + (long long)j * D + l * 8) : make_uint4(0, 0, 0, 0);
         }
         float mn = m;
 #pragma unroll
@@ -320,7 +338,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attention_kernel(
             const float p = exp2f(s[u] - mref);
             lsum += p;
             const float pr = bf16_round(p);   // same rounding point as the tensor-core kernel's P operand
-            const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&kv4[u]);
+            const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vv[u]);
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 const float2 f = __bfloat1622float2(v2[t]);
@@ -328,6 +346,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attention_kernel(
                 acc[2 * t + 1] += pr * f.y;
             }
         }
+#pragma unroll
+        for (int u = 0; u < DEC_UNROLL; ++u) kcur[u] = knext[u];
     }
     __shared__ float sm_m[DEC_WARPS * 2], sm_l[DEC_WARPS * 2], sm_acc[DEC_WARPS * 2][D];
     const int slot = warp * 2 + grp;

@@ -4,6 +4,7 @@
 // (modeling_dinov2.py:153-179) and the DDETR decoder self-attention (modeling_deformable_detr.py:453-516).
 #include "ptx.cuh"
 #include "capi_common.h"
+#include <cooperative_groups.h>
 
 namespace gb {
 
@@ -251,7 +252,8 @@ GROMA_API int32_t groma_attention(const void* q, int64_t q_bs, int64_t q_rs, con
 // Semantics = groma/model/groma.py:376-379 + eager LLaMA attention: every cached position < kv_len[b] is visible.
 namespace gb {
 
-constexpr int DEC_WARPS = 4, DEC_UNROLL = 4;   // 4 warps x 94 regs -> 5 CTAs/SM: all B*H CTAs resident in one wave
+constexpr int DEC_WARPS = 2, DEC_UNROLL = 4;   // 2 warps/CTA, 2 CTAs (one cluster) per (batch, head): 2*B*H CTAs all resident in one wave
+constexpr int DEC_SPLIT = 2;                   // keys are split over the CTAs of a cluster; partials merge through DSMEM
 
 // streaming 16-byte load that does not allocate in L1 (the KV cache is read once per step)
 __device__ __forceinline__ uint4 ld_nc_u4(const __nv_bfloat16* p) {
@@ -261,16 +263,22 @@ __device__ __forceinline__ uint4 ld_nc_u4(const __nv_bfloat16* p) {
 }
 
 template <int D>
-__global__ void __launch_bounds__(DEC_WARPS * 32) decode_attention_kernel(
+__global__ void __cluster_dims__(DEC_SPLIT, 1, 1) __launch_bounds__(DEC_WARPS * 32) decode_attention_kernel(
     const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc, const __nv_bfloat16* __restrict__ vc,
     __nv_bfloat16* __restrict__ out, const int* __restrict__ kv_len, int H, long long cap, float scale_log2) {
     static_assert(D == 128, "16 lanes x 8 dims");
-    const int h = blockIdx.x, b = blockIdx.y;
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = (int)cluster.block_rank();
+    const int h = blockIdx.x / DEC_SPLIT, b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane >> 4, l = lane & 15;
-    const int n = kv_len[b];
-    const __nv_bfloat16* kb = kc + ((long long)b * H + h) * cap * D;
-    const __nv_bfloat16* vb = vc + ((long long)b * H + h) * cap * D;
+    const int n_all = kv_len[b];
+    const int per = (n_all + DEC_SPLIT - 1) / DEC_SPLIT;
+    const int k_begin = min(crank * per, n_all);
+    const int n = min(n_all, k_begin + per) - k_begin;   // this CTA's keys: [k_begin, k_begin + n)
+    const __nv_bfloat16* kb = kc + (((long long)b * H + h) * cap + k_begin) * D;
+    const __nv_bfloat16* vb = vc + (((long long)b * H + h) * cap + k_begin) * D;
     float qf[8];
     {
         const uint4 qv = *reinterpret_cast<const uint4*>(q + ((long long)b * H + h) * D + l * 8);
@@ -350,12 +358,17 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attention_kernel(
         for (int u = 0; u < DEC_UNROLL; ++u) kcur[u] = knext[u];
     }
     __shared__ float sm_m[DEC_WARPS * 2], sm_l[DEC_WARPS * 2], sm_acc[DEC_WARPS * 2][D];
+    __shared__ float peer_m[DEC_SPLIT], peer_l[DEC_SPLIT], peer_acc[DEC_SPLIT][D];   // written by every rank into rank 0
     const int slot = warp * 2 + grp;
     if (l == 0) { sm_m[slot] = m; sm_l[slot] = lsum; }
 #pragma unroll
     for (int t = 0; t < 8; ++t) sm_acc[slot][l * 8 + t] = acc[t];
     __syncthreads();
-    if (threadIdx.x < D) {
+    // CTA-level merge -> (M, den, num[D]) sent to the leader CTA's shared memory (distributed shared memory)
+    float* r_m = cluster.map_shared_rank(peer_m, 0);
+    float* r_l = cluster.map_shared_rank(peer_l, 0);
+    float* r_acc = cluster.map_shared_rank(&peer_acc[0][0], 0);
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
         float M = -INFINITY;
 #pragma unroll
         for (int w = 0; w < DEC_WARPS * 2; ++w) M = fmaxf(M, sm_m[w]);
@@ -363,10 +376,27 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attention_kernel(
 #pragma unroll
         for (int w = 0; w < DEC_WARPS * 2; ++w) {
             const float c = (sm_m[w] == -INFINITY) ? 0.f : exp2f(sm_m[w] - M);
-            num += c * sm_acc[w][threadIdx.x];
+            num += c * sm_acc[w][d];
             den += c * sm_l[w];
         }
-        out[((long long)b * H + h) * D + threadIdx.x] = __float2bfloat16_rn(den > 0.f ? num / den : 0.f);
+        r_acc[crank * D + d] = num;
+        if (d == 0) { r_m[crank] = M; r_l[crank] = den; }
+    }
+    cluster.sync();
+    if (crank == 0) {
+        for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            float M = -INFINITY;
+#pragma unroll
+            for (int r = 0; r < DEC_SPLIT; ++r) M = fmaxf(M, peer_m[r]);
+            float num = 0.f, den = 0.f;
+#pragma unroll
+            for (int r = 0; r < DEC_SPLIT; ++r) {
+                const float c = (peer_m[r] == -INFINITY) ? 0.f : exp2f(peer_m[r] - M);
+                num += c * peer_acc[r][d];
+                den += c * peer_l[r];
+            }
+            out[((long long)b * H + h) * D + d] = __float2bfloat16_rn(den > 0.f ? num / den : 0.f);
+        }
     }
 }
 
@@ -377,7 +407,7 @@ GROMA_API int32_t groma_decode_attention(const void* q, const void* cache_k, con
                                          void* stream) {
     if (!q || !cache_k || !cache_v || !out || !kv_len || B <= 0 || H <= 0) return GROMA_ERR_ARG;
     if (D != 128) return GROMA_ERR_UNSUPPORTED;
-    gb::decode_attention_kernel<128><<<dim3(H, B), gb::DEC_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    gb::decode_attention_kernel<128><<<dim3(H * gb::DEC_SPLIT, B), gb::DEC_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(cache_k),
         reinterpret_cast<const __nv_bfloat16*>(cache_v), reinterpret_cast<__nv_bfloat16*>(out), kv_len, H, cap,
         scale * 1.4426950408889634f);

@@ -169,8 +169,9 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU (the B200 path has no CPU fallback)"
     torch.cuda.set_device(local)
     if world > 1:
+        import datetime
         import torch.distributed as dist
-        dist.init_process_group("nccl")
+        dist.init_process_group("nccl", timeout=datetime.timedelta(seconds=180))   # fail fast instead of a 10-minute watchdog
     from groma_b200 import ops as G
     from groma_b200.synth import make_state_dict
     from groma.model.groma import GromaConfig, GromaModel
@@ -234,14 +235,16 @@ def main():
 
     for _ in range(max(args.warmup, 1)):
         step(True)
-    if args.profile and rank == 0:
+    if args.profile:            # every rank runs the step (it contains collectives); rank 0 prints
         model.profile = []
         step(False)
         torch.cuda.synchronize()
         marks, model.profile = model.profile, None
         for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
-            print(f"[profile] {n1:>16s}: {e0.elapsed_time(e1):9.3f} ms", file=sys.stderr)
-        print(f"[profile] {'total':>16s}: {marks[0][1].elapsed_time(marks[-1][1]):9.3f} ms", file=sys.stderr)
+            if rank == 0:
+                print(f"[profile] {n1:>16s}: {e0.elapsed_time(e1):9.3f} ms", file=sys.stderr)
+        if rank == 0:
+            print(f"[profile] {'total':>16s}: {marks[0][1].elapsed_time(marks[-1][1]):9.3f} ms", file=sys.stderr)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -255,9 +258,7 @@ def main():
     gpu_launches = launches_dev // max(args.steps, 1) + replays * graph_kernels
 
     # ---- roofline of the dominant kernel: the swap-AB tcgen05 GEMM that streams the LLaMA weights during decode
-    roof = None
-    if rank == 0:
-        roof = decode_gemm_roofline(model, B, args, step)
+    roof = decode_gemm_roofline(model, B, args, step)   # all ranks: the step contains collectives; rank 0 reports its own
 
     if rank != 0:
         return

@@ -440,7 +440,8 @@ class GromaModel(torch.nn.Module):
         saved = {k: d[k].clone() for k in ("ids", "pos", "kv_len")}
         l0 = G.LAUNCHES
         with torch.cuda.stream(s):
-            with torch.cuda.graph(g, stream=s):
+            # thread_local: NCCL's watchdog thread may touch the CUDA API while this thread captures
+            with torch.cuda.graph(g, stream=s, capture_error_mode="thread_local"):
                 eng.decode_step(B)
         self._graph_kernels = G.LAUNCHES - l0
         torch.cuda.current_stream().wait_stream(s)

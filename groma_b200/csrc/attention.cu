@@ -267,6 +267,7 @@ __global__ void __cluster_dims__(DEC_SPLIT, 1, 1) __launch_bounds__(DEC_WARPS * 
     const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc, const __nv_bfloat16* __restrict__ vc,
     __nv_bfloat16* __restrict__ out, const int* __restrict__ kv_len, int H, long long cap, float scale_log2) {
     static_assert(D == 128, "16 lanes x 8 dims");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (int)cluster.block_rank();

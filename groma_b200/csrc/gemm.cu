@@ -59,6 +59,15 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
     const int n_tiles = (p.N + BN - 1) / BN;
     const int work = m_tiles * n_tiles * p.split_k;
     const int grid = work < num_sms() ? work : num_sms();
+    if (p.flags & GF_PDL) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN>, p) == cudaSuccess ? GROMA_OK : GROMA_ERR_CUDA;
+    }
     gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? GROMA_OK : GROMA_ERR_CUDA;
 }
@@ -69,6 +78,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, i
                                      const float* __restrict__ bias, const float* __restrict__ gamma,
                                      const __nv_bfloat16* __restrict__ residual, void* __restrict__ out, long long ld_m,
                                      long long ld_n) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const bool bias_m0 = flags & GF_BIAS_ALONG_M;
     const long long total = (act == ACT_SWIGLU) ? (bias_m0 ? (long long)(M / 2) * N : (long long)M * (N / 2)) : (long long)M * N;
     const bool bias_m = flags & GF_BIAS_ALONG_M;
@@ -133,6 +143,7 @@ GROMA_API int32_t groma_gemm_bf16(const void* A, int64_t a_rows, int64_t lda, co
     if (act == ACT_SWIGLU && !(flags & GF_BIAS_ALONG_M) && (N & 1)) return GROMA_ERR_ARG;
     if (act == ACT_SWIGLU && (flags & GF_BIAS_ALONG_M) && (M & 1)) return GROMA_ERR_ARG;
     if (num_taps > 1 && (K % GEMM_BK) != 0) return GROMA_ERR_ARG;
+    if ((flags & GF_A_TILED) && (num_taps != 1 || lda != GEMM_BK)) return GROMA_ERR_ARG;
 
     int bn = block_n;
     if (bn == 0) {
@@ -148,7 +159,7 @@ GROMA_API int32_t groma_gemm_bf16(const void* A, int64_t a_rows, int64_t lda, co
         }
     }
     GemmParams p;
-    int rc = make_tma_2d(&p.tma_a, A, (uint64_t)a_rows, (uint64_t)K, (uint64_t)lda, GEMM_BM);
+    int rc = make_tma_2d(&p.tma_a, A, (uint64_t)a_rows, (flags & GF_A_TILED) ? (uint64_t)GEMM_BK : (uint64_t)K, (uint64_t)lda, GEMM_BM);
     if (rc) return rc;
     rc = make_tma_2d(&p.tma_b, B, (uint64_t)b_rows, (uint64_t)K * num_taps, (uint64_t)ldb, (uint32_t)bn);
     if (rc) return rc;

@@ -22,6 +22,8 @@ enum GemmFlags : int {
     GF_PARTIAL = 4,       // store raw fp32 accumulators to ws[split][m][n] (split-K / deferred epilogue)
     GF_CONV_ROWS = 8,     // rows are pixels of zero-bordered [img][hp][wp] maps: skip border rows
     GF_CONV_COMPACT = 16, // with GF_CONV_ROWS: write row index of the un-padded [img][h][w] layout
+    GF_A_TILED = 32,      // A is pre-tiled in HBM: [m_tile][k_block][128 rows][64 cols] -> every TMA load is one contiguous 16 KB
+    GF_PDL = 64,          // launched with programmatic stream serialisation: A (weights) is prefetched before griddepcontrol.wait
 };
 
 struct GemmParams {
@@ -127,23 +129,59 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-                const int split = w % p.split_k;
-                const int tile = w / p.split_k;
-                int m_blk, n_blk;
-                tile_coords(tile, m_tiles, n_tiles, m_blk, n_blk);
-                const int it0 = split * iters_per_split;
-                const int it1 = min(total_iters, it0 + iters_per_split);
-                for (int it = it0; it < it1; ++it) {
-                    const int tap = it / kb_per_tap, kb = it - tap * kb_per_tap;
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-                    uint8_t* sb = sa + Cfg::A_BYTES;
-                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                    tma_load_2d(sa, &p.tma_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM + p.a_row_off[tap]);
-                    tma_load_2d(sb, &p.tma_b, &full_bar[stage], tap * p.K + kb * GEMM_BK, n_blk * BN);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            const bool a_tiled = (p.flags & GF_A_TILED) != 0;
+            // work iterator over this CTA's (work item, k-iteration) pairs
+            int w = blockIdx.x, it = 0, it1 = 0, m_blk = 0, n_blk = 0;
+            auto load_work = [&]() {
+                while (w < num_work) {
+                    const int split = w % p.split_k;
+                    const int tile = w / p.split_k;
+                    tile_coords(tile, m_tiles, n_tiles, m_blk, n_blk);
+                    it = split * iters_per_split;
+                    it1 = min(total_iters, it + iters_per_split);
+                    if (it < it1) return true;
+                    w += gridDim.x;   // empty split: nothing to load
                 }
+                return false;
+            };
+            auto a_coords = [&](int tap, int kb, int& c0, int& c1) {
+                if (a_tiled) { c0 = 0; c1 = (m_blk * kb_per_tap + kb) * GEMM_BM; }
+                else { c0 = kb * GEMM_BK; c1 = m_blk * GEMM_BM + p.a_row_off[tap]; }
+            };
+            bool have = load_work();
+            if (p.flags & GF_PDL) {
+                // The A operand (weights) does not depend on the previous kernel: fill the ring with A tiles first, only then
+                // wait for the producer of B (activations).  Hides launch + prologue + first-byte latency of every decode GEMM.
+                int bc0[STAGES], bc1[STAGES];
+                int issued = 0;
+                while (have && issued < STAGES) {
+                    const int tap = it / kb_per_tap, kb = it - tap * kb_per_tap;
+                    int c0, c1;
+                    a_coords(tap, kb, c0, c1);
+                    mbar_expect_tx(&full_bar[issued], Cfg::STAGE_BYTES);
+                    tma_load_2d(smem + issued * Cfg::STAGE_BYTES, &p.tma_a, &full_bar[issued], c0, c1);
+                    bc0[issued] = tap * p.K + kb * GEMM_BK;
+                    bc1[issued] = n_blk * BN;
+                    ++issued;
+                    if (++it >= it1) { w += gridDim.x; have = load_work(); }
+                }
+                asm volatile("griddepcontrol.wait;" ::: "memory");
+                for (int i = 0; i < issued; ++i)
+                    tma_load_2d(smem + i * Cfg::STAGE_BYTES + Cfg::A_BYTES, &p.tma_b, &full_bar[i], bc0[i], bc1[i]);
+                if (issued == STAGES) { stage = 0; phase = 1; } else { stage = issued; }
+            }
+            while (have) {
+                const int tap = it / kb_per_tap, kb = it - tap * kb_per_tap;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                uint8_t* sb = sa + Cfg::A_BYTES;
+                int c0, c1;
+                a_coords(tap, kb, c0, c1);
+                mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                tma_load_2d(sa, &p.tma_a, &full_bar[stage], c0, c1);
+                tma_load_2d(sb, &p.tma_b, &full_bar[stage], tap * p.K + kb * GEMM_BK, n_blk * BN);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                if (++it >= it1) { w += gridDim.x; have = load_work(); }
             }
         }
     } else if (warp == 1) {

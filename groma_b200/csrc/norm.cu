@@ -29,6 +29,7 @@ template <int VPT>
 __global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ r,
                                const float* __restrict__ w, __nv_bfloat16* __restrict__ y,
                                __nv_bfloat16* __restrict__ h_out, int dim, float eps) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // a PDL-launched GEMM may start prefetching its weights now
     __shared__ float red[32];
     const long long row = blockIdx.x;
     const int nvec = dim >> 3;

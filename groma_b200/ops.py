@@ -98,13 +98,30 @@ def gemm_splitk(a: torch.Tensor, w: torch.Tensor, split_k: int, *, bias=None, ac
     return out
 
 
-def gemm_swap_ab(x: torch.Tensor, w: torch.Tensor, ws: torch.Tensor, split_k: int = 1, block_n: int = 0) -> torch.Tensor:
+GF_A_TILED, GF_PDL = 32, 64
+
+
+def tile_weight(w: torch.Tensor) -> torch.Tensor:
+    """[N, K] -> tile-major [(N/128)*(K/64)*128, 64] (zero padded): every 128x64 TMA tile is one contiguous 16 KB."""
+    N, K = w.shape
+    Np, Kp = (N + 127) // 128 * 128, (K + 63) // 64 * 64
+    if (Np, Kp) != (N, K):
+        wp = torch.zeros((Np, Kp), dtype=w.dtype, device=w.device)
+        wp[:N, :K] = w
+        w = wp
+    return w.view(Np // 128, 128, Kp // 64, 64).permute(0, 2, 1, 3).contiguous().view(-1, 64)
+
+
+def gemm_swap_ab(x: torch.Tensor, w: torch.Tensor, ws: torch.Tensor, split_k: int = 1, block_n: int = 0,
+                 n_rows: Optional[int] = None, tiled: bool = False, pdl: bool = False) -> torch.Tensor:
     """Skinny-M GEMM for decode: computes (w[N,K] @ x[M,K]^T) with the weight as the 128-row MMA operand and the
-    M<=256 activation rows as the MMA N dimension; raw fp32 partials land in ws[split][N][M]."""
+    M<=256 activation rows as the MMA N dimension; raw fp32 partials land in ws[split][N][M].
+    tiled: w is the output of tile_weight() (then n_rows = logical N).  pdl: programmatic dependent launch."""
     _bf16(x, "x"); _bf16(w, "w")
     M, K = x.shape
-    N = w.shape[0]
-    rc = _L().groma_gemm_bf16(_p(w), N, w.stride(0), _p(x), M, x.stride(0), N, M, K, 1, None, None, 0, 0, GF_PARTIAL,
+    N = w.shape[0] if n_rows is None else n_rows
+    flags = GF_PARTIAL | (GF_A_TILED if tiled else 0) | (GF_PDL if pdl else 0)
+    rc = _L().groma_gemm_bf16(_p(w), w.shape[0], w.stride(0), _p(x), M, x.stride(0), N, M, K, 1, None, None, 0, 0, flags,
                               ACT_NONE, None, None, None, _p(ws), split_k, None, 0, 0, block_n, _stream())
     _chk(rc, "groma_gemm_bf16(swap-ab)")
     return ws

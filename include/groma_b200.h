@@ -36,6 +36,8 @@ extern "C" {
 #define GROMA_GF_PARTIAL 4
 #define GROMA_GF_CONV_ROWS 8
 #define GROMA_GF_CONV_COMPACT 16
+#define GROMA_GF_A_TILED 32 /* A pre-tiled [m_tile][k_block][128][64] (lda must be 64): each TMA load is 16 KB contiguous */
+#define GROMA_GF_PDL 64     /* programmatic dependent launch: A tiles are prefetched before waiting for the previous kernel */
 
 /* D[M,N] = sum_{t<num_taps} A[m + a_row_off[t], 0:K] . B[n, t*K : (t+1)*K]   (+ bias, act, *gamma, + residual)
  * tcgen05/TMEM/TMA GEMM.  Replaces every torch.nn.Linear / nn.Conv2d(1x1, 3x3 pad 1) call on the path:

@@ -268,6 +268,7 @@ __global__ void __cluster_dims__(DEC_SPLIT, 1, 1) __launch_bounds__(DEC_WARPS * 
     __nv_bfloat16* __restrict__ out, const int* __restrict__ kv_len, int H, long long cap, float scale_log2) {
     static_assert(D == 128, "16 lanes x 8 dims");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // no-op unless launched with programmatic serialisation
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (int)cluster.block_rank();
@@ -405,12 +406,19 @@ __global__ void __cluster_dims__(DEC_SPLIT, 1, 1) __launch_bounds__(DEC_WARPS * 
 
 GROMA_API int32_t groma_decode_attention(const void* q, const void* cache_k, const void* cache_v, void* out,
                                          const int32_t* kv_len, int32_t B, int32_t H, int32_t D, int64_t cap, float scale,
-                                         void* stream) {
+                                         int32_t pdl, void* stream) {
     if (!q || !cache_k || !cache_v || !out || !kv_len || B <= 0 || H <= 0) return GROMA_ERR_ARG;
     if (D != 128) return GROMA_ERR_UNSUPPORTED;
-    gb::decode_attention_kernel<128><<<dim3(H * gb::DEC_SPLIT, B), gb::DEC_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(cache_k),
-        reinterpret_cast<const __nv_bfloat16*>(cache_v), reinterpret_cast<__nv_bfloat16*>(out), kv_len, H, cap,
-        scale * 1.4426950408889634f);
-    return GROMA_LAUNCH_CHECK();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(H * gb::DEC_SPLIT, B); cfg.blockDim = dim3(gb::DEC_WARPS * 32); cfg.dynamicSmemBytes = 0;
+    cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    if (pdl) { cfg.attrs = attr; cfg.numAttrs = 1; }
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, gb::decode_attention_kernel<128>, reinterpret_cast<const __nv_bfloat16*>(q),
+                                             reinterpret_cast<const __nv_bfloat16*>(cache_k), reinterpret_cast<const __nv_bfloat16*>(cache_v),
+                                             reinterpret_cast<__nv_bfloat16*>(out), kv_len, (int)H, (long long)cap,
+                                             scale * 1.4426950408889634f);
+    return e == cudaSuccess ? GROMA_OK : GROMA_ERR_CUDA;
 }

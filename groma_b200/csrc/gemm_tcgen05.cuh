@@ -24,6 +24,7 @@ enum GemmFlags : int {
     GF_CONV_COMPACT = 16, // with GF_CONV_ROWS: write row index of the un-padded [img][h][w] layout
     GF_A_TILED = 32,      // A is pre-tiled in HBM: [m_tile][k_block][128 rows][64 cols] -> every TMA load is one contiguous 16 KB
     GF_PDL = 64,          // launched with programmatic stream serialisation: A (weights) is prefetched before griddepcontrol.wait
+    GF_PARTIAL_T = 128,   // with GF_PARTIAL: partials stored transposed, ws[split][n][m] (swap-AB decode: token-major rows)
 };
 
 struct GemmParams {
@@ -267,6 +268,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
                 if (!has_work) {
 #pragma unroll
                     for (int j = 0; j < CHUNK; ++j) v[j] = 0u;
+                }
+                if (partial && (p.flags & GF_PARTIAL_T)) {
+                    // lanes = consecutive rows m -> each store instruction writes 128 contiguous bytes of ws[split][n][:]
+                    float* dst = p.ws + ((long long)split * p.N + n0) * p.M + out_row;
+                    _Pragma("unroll") for (int j = 0; j < CHUNK; ++j) if (n0 + j < p.N) dst[(long long)j * p.M] = __uint_as_float(v[j]);
+                    continue;
                 }
                 if (partial) {
                     float* dst = p.ws + ((long long)split * p.M + out_row) * p.N + n0;

@@ -35,6 +35,8 @@ class GromaEngine:
         self.stages: Dict[str, torch.Tensor] = {}
         self.keep_stages = False
         self.fused_splitk = False
+        self.fused_decode = True     # fused reduce epilogues + PDL in the decode step
+        self.use_pdl = True
         self.timing_hook = None   # bench.py: list collecting (start_event, end_event, algorithmic_bytes) per swap-AB GEMM
 
     # ------------------------------------------------------------------------------------------ weights
@@ -517,7 +519,57 @@ class GromaEngine:
     def decode_step(self, B: int) -> torch.Tensor:
         """One greedy decode step for the whole batch (groma.py:376-402 + HF greedy argmax): reads d['ids'], appends K/V at
         *pos, attends to all kv_len[b] cached positions (all-ones mask, T7), writes next ids back to d['ids'].
-        Every shape-dependent scalar lives on the device, so the step is CUDA-graph capturable."""
+        Every shape-dependent scalar lives on the device, so the step is CUDA-graph capturable.
+        Per layer: 4 swap-AB tcgen05 GEMMs (weights prefetched under programmatic dependent launch), 4 fused reduce
+        epilogues (RoPE+KV append / residual+RMSNorm / SwiGLU / residual+next RMSNorm) and the cluster decode attention."""
+        if not self.fused_decode:
+            return self._decode_step_unfused(B)
+        cfg, w = self.cfg, self.w
+        d = self._decode_buffers(B)
+        nh, hd, Hd = cfg.llm_heads, cfg.head_dim, cfg.llm_hidden
+        sp = self._decode_splits()
+        pdl = self.use_pdl
+        G.gather_rows(d["ids"], w["embed"], w["new_embed"], cfg.vocab, out=d["x"])
+        x, y = d["x"], d["y"]
+        G.rmsnorm(x, w["llm.0.ln1"], cfg.rms_eps, out=y)
+
+        def gemm(inp, wname, split):
+            W = w[wname]
+            ws = d["ws"][: split * W.shape[0] * B].view(split, B, W.shape[0])
+            if self.timing_hook is not None:
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+            G.gemm_swap_ab(inp, W, ws, split_k=split, pdl=pdl, transposed=True)
+            if self.timing_hook is not None:
+                ev1.record()
+                self.timing_hook.append((ev0, ev1, W.numel() * 2 + inp.numel() * 2 + ws.numel() * 4))
+            return ws
+
+        for i in range(cfg.llm_layers):
+            o = f"llm.{i}."
+            kc, vc = self.kv[i, 0], self.kv[i, 1]
+            ws = gemm(y, o + "qkv.w", sp["qkv"])
+            G.decode_reduce_rope_kv(ws, d["q"], kc, vc, self.rope_cos, self.rope_sin, d["pos"], nh, hd, pdl=pdl)
+            if hd == 128:
+                G.decode_attention(d["q"], kc, vc, d["kv_len"], 1.0 / math.sqrt(hd), d["a"], pdl=pdl)
+            else:
+                G.attention(d["q"].reshape(B, 1, nh, hd), kc, vc, causal=False, scale=1.0 / math.sqrt(hd), kv_len=d["kv_len"],
+                            out=d["a"], sk=self.kv_cap)
+            ws = gemm(d["a"].reshape(B, Hd), o + "o.w", sp["o"])
+            G.decode_reduce_norm(ws, x, w[o + "ln2"], y, cfg.rms_eps, pdl=pdl)
+            ws = gemm(y, o + "gu.w", sp["gu"])
+            G.decode_reduce_swiglu(ws, d["gu"], pdl=pdl)
+            ws = gemm(d["gu"], o + "down.w", sp["down"])
+            nxt = w[f"llm.{i + 1}.ln1"] if i + 1 < cfg.llm_layers else w["llm.norm"]
+            G.decode_reduce_norm(ws, x, nxt, y, cfg.rms_eps, pdl=pdl)
+        ws = gemm(y, "head.w", sp["head"])
+        G.splitk_reduce(ws, d["logits"])
+        G.argmax(d["logits"], out=d["ids"])
+        G.decode_advance(d["pos"], d["kv_len"])
+        return d["logits"]
+
+    def _decode_step_unfused(self, B: int) -> torch.Tensor:
+        """Reference arrangement of the same step with stand-alone reduce / norm / RoPE kernels (kept for A/B tests)."""
         cfg, w = self.cfg, self.w
         d = self._decode_buffers(B)
         nh, hd, Hd = cfg.llm_heads, cfg.head_dim, cfg.llm_hidden

@@ -98,7 +98,7 @@ def gemm_splitk(a: torch.Tensor, w: torch.Tensor, split_k: int, *, bias=None, ac
     return out
 
 
-GF_A_TILED, GF_PDL = 32, 64
+GF_A_TILED, GF_PDL, GF_PARTIAL_T = 32, 64, 128
 
 
 def tile_weight(w: torch.Tensor) -> torch.Tensor:
@@ -113,14 +113,14 @@ def tile_weight(w: torch.Tensor) -> torch.Tensor:
 
 
 def gemm_swap_ab(x: torch.Tensor, w: torch.Tensor, ws: torch.Tensor, split_k: int = 1, block_n: int = 0,
-                 n_rows: Optional[int] = None, tiled: bool = False, pdl: bool = False) -> torch.Tensor:
+                 n_rows: Optional[int] = None, tiled: bool = False, pdl: bool = False, transposed: bool = False) -> torch.Tensor:
     """Skinny-M GEMM for decode: computes (w[N,K] @ x[M,K]^T) with the weight as the 128-row MMA operand and the
     M<=256 activation rows as the MMA N dimension; raw fp32 partials land in ws[split][N][M].
     tiled: w is the output of tile_weight() (then n_rows = logical N).  pdl: programmatic dependent launch."""
     _bf16(x, "x"); _bf16(w, "w")
     M, K = x.shape
     N = w.shape[0] if n_rows is None else n_rows
-    flags = GF_PARTIAL | (GF_A_TILED if tiled else 0) | (GF_PDL if pdl else 0)
+    flags = GF_PARTIAL | (GF_A_TILED if tiled else 0) | (GF_PDL if pdl else 0) | (GF_PARTIAL_T if transposed else 0)
     rc = _L().groma_gemm_bf16(_p(w), w.shape[0], w.stride(0), _p(x), M, x.stride(0), N, M, K, 1, None, None, 0, 0, flags,
                               ACT_NONE, None, None, None, _p(ws), split_k, None, 0, 0, block_n, _stream())
     _chk(rc, "groma_gemm_bf16(swap-ab)")
@@ -206,12 +206,12 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, causal: bool
 
 
 def decode_attention(q: torch.Tensor, cache_k: torch.Tensor, cache_v: torch.Tensor, kv_len: torch.Tensor, scale: float,
-                     out: torch.Tensor) -> torch.Tensor:
+                     out: torch.Tensor, pdl: bool = False) -> torch.Tensor:
     """q/out [B, H*D] bf16, cache_k/v [B, H, cap, D] contiguous, kv_len int32 [B] on device."""
     _bf16(q, "q")
     B, H, cap, D = cache_k.shape
     assert cache_k.is_contiguous() and cache_v.is_contiguous() and q.is_contiguous() and out.is_contiguous()
-    rc = _L().groma_decode_attention(_p(q), _p(cache_k), _p(cache_v), _p(out), _p(kv_len), B, H, D, cap, float(scale), _stream())
+    rc = _L().groma_decode_attention(_p(q), _p(cache_k), _p(cache_v), _p(out), _p(kv_len), B, H, D, cap, float(scale), 1 if pdl else 0, _stream())
     _chk(rc, "groma_decode_attention")
     return out
 
@@ -470,3 +470,23 @@ def linear_smallk(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], r
 
 def decode_advance(pos: torch.Tensor, kv_len: torch.Tensor):
     _chk(_L().groma_decode_advance(_p(pos), _p(kv_len), kv_len.numel(), _stream()), "groma_decode_advance")
+
+
+def decode_reduce_norm(ws: torch.Tensor, x: torch.Tensor, w: torch.Tensor, y: torch.Tensor, eps: float, pdl: bool = True):
+    """ws [S, B, N] fp32 token-major partials; x [B, N] bf16 residual stream (updated in place); y = RMSNorm(x) * w."""
+    S, B, N = ws.shape
+    _chk(_L().groma_decode_reduce_norm(_p(ws), S, B, N, _p(x), _p(w), _p(y), float(eps), 1 if pdl else 0, _stream()),
+         "groma_decode_reduce_norm")
+
+
+def decode_reduce_swiglu(ws: torch.Tensor, out: torch.Tensor, pdl: bool = True):
+    S, B, N = ws.shape
+    _chk(_L().groma_decode_reduce_swiglu(_p(ws), S, B, N, _p(out), 1 if pdl else 0, _stream()), "groma_decode_reduce_swiglu")
+
+
+def decode_reduce_rope_kv(ws: torch.Tensor, q_out: torch.Tensor, cache_k: torch.Tensor, cache_v: torch.Tensor, cos_t: torch.Tensor,
+                          sin_t: torch.Tensor, pos_ptr: torch.Tensor, H: int, D: int, pdl: bool = True):
+    S, B, N = ws.shape
+    assert N == 3 * H * D
+    _chk(_L().groma_decode_reduce_rope_kv(_p(ws), S, B, H, D, _p(q_out), _p(cache_k), _p(cache_v), _p(cos_t), _p(sin_t),
+                                          _p(pos_ptr), cache_k.shape[2], 1 if pdl else 0, _stream()), "groma_decode_reduce_rope_kv")

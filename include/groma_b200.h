@@ -37,6 +37,7 @@ extern "C" {
 #define GROMA_GF_CONV_ROWS 8
 #define GROMA_GF_CONV_COMPACT 16
 #define GROMA_GF_A_TILED 32 /* A pre-tiled [m_tile][k_block][128][64] (lda must be 64): each TMA load is 16 KB contiguous */
+#define GROMA_GF_PARTIAL_T 128 /* partials transposed: ws[split][n][m] */
 #define GROMA_GF_PDL 64     /* programmatic dependent launch: A tiles are prefetched before waiting for the previous kernel */
 
 /* D[M,N] = sum_{t<num_taps} A[m + a_row_off[t], 0:K] . B[n, t*K : (t+1)*K]   (+ bias, act, *gamma, + residual)
@@ -77,7 +78,7 @@ int32_t groma_attention(const void* q, int64_t q_bs, int64_t q_rs, const void* k
 /* Single-query (decode) attention over the KV cache: every cached position < kv_len[b] is visible (the all-ones mask of
  * groma/model/groma.py:376-379).  q, out [B, H*D]; cache_k/v [B, H, cap, D]; D = 128.  HBM-bound SIMT kernel. */
 int32_t groma_decode_attention(const void* q, const void* cache_k, const void* cache_v, void* out, const int32_t* kv_len,
-                               int32_t B, int32_t H, int32_t D, int64_t cap, float scale, void* stream);
+                               int32_t B, int32_t H, int32_t D, int64_t cap, float scale, int32_t pdl, void* stream);
 
 /* y = w * bf16(h * rsqrt(mean(h^2)+eps)), h = bf16(x + residual) (h_out optional).  LlamaRMSNorm,
  * $HF/models/llama/modeling_llama.py:53-70 (+ the residual add of :292-340). */
@@ -170,6 +171,18 @@ int32_t groma_linear_smallk(const float* x, const float* w, const float* b, void
 
 /* device-side decode bookkeeping (*pos += 1; kv_len[b] += 1) so a decode step is CUDA-graph capturable. */
 int32_t groma_decode_advance(int32_t* pos, int32_t* kv_len, int32_t B, void* stream);
+
+/* Fused decode epilogues over token-major split-K partials ws[split][token][feature] (GROMA_GF_PARTIAL_T); pdl != 0
+ * launches them with programmatic stream serialisation (they wait for their producer in-kernel).
+ *   reduce_norm   : x = bf16(sum + x) in place; y = LlamaRMSNorm(x)            (modeling_llama.py:292-340,53-70)
+ *   reduce_swiglu : out[:, j] = silu(sum[2j]) * sum[2j+1]                        (modeling_llama.py:171-184)
+ *   reduce_rope_kv: RoPE(q,k) at *pos_ptr, q -> q_out, k/v -> cache[b,h,*pos_ptr] (modeling_llama.py:138-168,225-289) */
+int32_t groma_decode_reduce_norm(const float* ws, int32_t splits, int32_t B, int32_t N, void* x, const float* w, void* y,
+                                 float eps, int32_t pdl, void* stream);
+int32_t groma_decode_reduce_swiglu(const float* ws, int32_t splits, int32_t B, int32_t N, void* out, int32_t pdl, void* stream);
+int32_t groma_decode_reduce_rope_kv(const float* ws, int32_t splits, int32_t B, int32_t H, int32_t D, void* q_out, void* cache_k,
+                                    void* cache_v, const float* cos_t, const float* sin_t, const int32_t* pos_ptr, int64_t cap,
+                                    int32_t pdl, void* stream);
 
 /* greedy next-token argmax over fp32 logits (HF greedy_search). */
 int32_t groma_argmax(const float* logits, int64_t* out, int32_t rows, int32_t V, int64_t ld, void* stream);

@@ -85,3 +85,30 @@ def test_swap_ab_fused_finish(G):
             r = res.clone().cuda()
             G.gemm_swap_ab_fused(x.cuda(), w.cuda(), ws, cnt, split, r, residual=r)
             assert ((r.float().cpu() - (ref + res.float())).abs().max() / (ref + res.float()).abs().max()) < 6e-3
+
+
+def test_fused_decode_step_is_bit_identical_to_unfused():
+    """The fused reduce epilogues + programmatic dependent launch must not change a single bit of the decode logits."""
+    from groma.model.groma import GromaConfig, GromaModel
+    from groma_b200.config import SyntheticTokenizer, tiny_config
+    from groma_b200.synth import make_state_dict
+    cfg = tiny_config(box_score_thres=0.0)
+    tok = SyntheticTokenizer(cfg.vocab)
+    m = GromaModel(GromaConfig.from_path_config(cfg), state_dict=make_state_dict(cfg, seed=0), path_config=cfg)
+    m.init_special_token_id(tok)
+    g = torch.Generator().manual_seed(3)
+    images = torch.randn(2, 3, 448, 448, generator=g)
+    ids = torch.randint(10, cfg.vocab, (2, 16), generator=g)
+    ids[:, 2] = tok.map["<image>"]; ids[:, 9] = tok.map["<region>"]
+    boxes = [torch.rand(4, 4, generator=g) * 0.6 + 0.2, torch.rand(6, 4, generator=g) * 0.6 + 0.2]
+    runs = {}
+    for fused, pdl, graph in [(False, False, False), (True, False, False), (True, True, False), (True, True, True)]:
+        m.engine.fused_decode, m.engine.use_pdl, m.use_cuda_graph = fused, pdl, graph
+        m._graph = None
+        out = m.generate(ids.clone().cuda(), images=images.cuda(), max_new_tokens=6, return_dict_in_generate=True,
+                         _selected_override=boxes, _keep_logits=True)
+        runs[(fused, pdl, graph)] = (out.sequences.cpu(), torch.stack([x.cpu() for x in m._step_logits], 1))
+    base_seq, base_lg = runs[(False, False, False)]
+    for k, (seq, lg) in runs.items():
+        assert torch.equal(seq, base_seq), k
+        assert torch.equal(lg, base_lg), k

@@ -260,6 +260,10 @@ def main():
     # ---- roofline of the dominant kernel: the swap-AB tcgen05 GEMM that streams the LLaMA weights during decode
     roof = decode_gemm_roofline(model, B, args, step)   # all ranks: the step contains collectives; rank 0 reports its own
 
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     n_img = B * world * args.steps

@@ -5,6 +5,7 @@
 #include "ptx.cuh"
 #include "capi_common.h"
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 namespace gb {
 
@@ -252,7 +253,7 @@ GROMA_API int32_t groma_attention(const void* q, int64_t q_bs, int64_t q_rs, con
 // Semantics = groma/model/groma.py:376-379 + eager LLaMA attention: every cached position < kv_len[b] is visible.
 namespace gb {
 
-constexpr int DEC_WARPS = 2, DEC_UNROLL = 4;   // 2 warps/CTA, 2 CTAs (one cluster) per (batch, head): 2*B*H CTAs all resident in one wave
+constexpr int DEC_WARPS = 2;   // 2 warps/CTA, 2 CTAs (one cluster) per (batch, head): 2*B*H CTAs all resident in one wave
 constexpr int DEC_SPLIT = 2;                   // keys are split over the CTAs of a cluster; partials merge through DSMEM
 
 // streaming 16-byte load that does not allocate in L1 (the KV cache is read once per step)
@@ -262,7 +263,7 @@ __device__ __forceinline__ uint4 ld_nc_u4(const __nv_bfloat16* p) {
     return r;
 }
 
-template <int D>
+template <int D, int DEC_UNROLL>
 __global__ void __cluster_dims__(DEC_SPLIT, 1, 1) __launch_bounds__(DEC_WARPS * 32) decode_attention_kernel(
     const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc, const __nv_bfloat16* __restrict__ vc,
     __nv_bfloat16* __restrict__ out, const int* __restrict__ kv_len, int H, long long cap, float scale_log2) {
@@ -416,9 +417,17 @@ GROMA_API int32_t groma_decode_attention(const void* q, const void* cache_k, con
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     if (pdl) { cfg.attrs = attr; cfg.numAttrs = 1; }
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, gb::decode_attention_kernel<128>, reinterpret_cast<const __nv_bfloat16*>(q),
-                                             reinterpret_cast<const __nv_bfloat16*>(cache_k), reinterpret_cast<const __nv_bfloat16*>(cache_v),
-                                             reinterpret_cast<__nv_bfloat16*>(out), kv_len, (int)H, (long long)cap,
-                                             scale * 1.4426950408889634f);
+    static int unroll = 0;   // loads in flight per lane = 2 * unroll x 16 B; GROMA_DEC_UNROLL overrides for tuning
+    if (!unroll) { const char* ev = getenv("GROMA_DEC_UNROLL"); unroll = ev ? atoi(ev) : 4; }
+    auto Q = reinterpret_cast<const __nv_bfloat16*>(q);
+    auto K = reinterpret_cast<const __nv_bfloat16*>(cache_k);
+    auto V = reinterpret_cast<const __nv_bfloat16*>(cache_v);
+    auto O = reinterpret_cast<__nv_bfloat16*>(out);
+    const float sl2 = scale * 1.4426950408889634f;
+    cudaError_t e;
+    if (unroll == 8) e = cudaLaunchKernelEx(&cfg, gb::decode_attention_kernel<128, 8>, Q, K, V, O, kv_len, (int)H, (long long)cap, sl2);
+    else if (unroll == 6) e = cudaLaunchKernelEx(&cfg, gb::decode_attention_kernel<128, 6>, Q, K, V, O, kv_len, (int)H, (long long)cap, sl2);
+    else if (unroll == 2) e = cudaLaunchKernelEx(&cfg, gb::decode_attention_kernel<128, 2>, Q, K, V, O, kv_len, (int)H, (long long)cap, sl2);
+    else e = cudaLaunchKernelEx(&cfg, gb::decode_attention_kernel<128, 4>, Q, K, V, O, kv_len, (int)H, (long long)cap, sl2);
     return e == cudaSuccess ? GROMA_OK : GROMA_ERR_CUDA;
 }

@@ -165,28 +165,47 @@ __global__ void rope_kv_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloa
                                int D, int pos0, const int* __restrict__ pos_ptr, long long ctx_cap) {
     const int half = D / 2;
     if (pos_ptr) pos0 = *pos_ptr;
-    const long long total = (long long)B * T * H * half;
+    const int hv = half >> 3;   // 16-byte vectors per half head
+    const long long total = (long long)B * T * H * hv;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int j = i % half;
-        long long r = i / half;
+        const int jv = i % hv;
+        long long r = i / hv;
         const int h = r % H; r /= H;
         const int t = r % T, b = r / T;
-        const int pos = pos0 + t;
-        const float c = cos_t[(long long)pos * half + j], s = sin_t[(long long)pos * half + j];
+        const int pos = pos0 + t, j = jv * 8;
+        float c[8], s[8];
+        *reinterpret_cast<float4*>(c) = *reinterpret_cast<const float4*>(cos_t + (long long)pos * half + j);
+        *reinterpret_cast<float4*>(c + 4) = *reinterpret_cast<const float4*>(cos_t + (long long)pos * half + j + 4);
+        *reinterpret_cast<float4*>(s) = *reinterpret_cast<const float4*>(sin_t + (long long)pos * half + j);
+        *reinterpret_cast<float4*>(s + 4) = *reinterpret_cast<const float4*>(sin_t + (long long)pos * half + j + 4);
         const long long row = ((long long)b * T + t) * 3 * H * D;
-        const __nv_bfloat16* qp = qkv + row + h * D;
-        const __nv_bfloat16* kp = qkv + row + (long long)H * D + h * D;
-        const __nv_bfloat16* vp = qkv + row + 2LL * H * D + h * D;
-        const float q1 = __bfloat162float(qp[j]), q2 = __bfloat162float(qp[j + half]);
-        const float k1 = __bfloat162float(kp[j]), k2 = __bfloat162float(kp[j + half]);
-        __nv_bfloat16* qo = q_out + ((long long)b * T + t) * H * D + h * D;
-        qo[j] = __float2bfloat16_rn(q1 * c - q2 * s);
-        qo[j + half] = __float2bfloat16_rn(q2 * c + q1 * s);
-        const long long co = (((long long)b * H + h) * ctx_cap + pos) * D;
-        cache_k[co + j] = __float2bfloat16_rn(k1 * c - k2 * s);
-        cache_k[co + j + half] = __float2bfloat16_rn(k2 * c + k1 * s);
-        cache_v[co + j] = vp[j];
-        cache_v[co + j + half] = vp[j + half];
+        const __nv_bfloat16* qp = qkv + row + h * D + j;
+        const __nv_bfloat16* kp = qkv + row + (long long)H * D + h * D + j;
+        const __nv_bfloat16* vp = qkv + row + 2LL * H * D + h * D + j;
+        const uint4 q1v = *reinterpret_cast<const uint4*>(qp), q2v = *reinterpret_cast<const uint4*>(qp + half);
+        const uint4 k1v = *reinterpret_cast<const uint4*>(kp), k2v = *reinterpret_cast<const uint4*>(kp + half);
+        const __nv_bfloat162* q1 = reinterpret_cast<const __nv_bfloat162*>(&q1v);
+        const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&q2v);
+        const __nv_bfloat162* k1 = reinterpret_cast<const __nv_bfloat162*>(&k1v);
+        const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&k2v);
+        uint32_t qa[4], qb[4], ka[4], kb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float2 a = __bfloat1622float2(q1[u]), bq = __bfloat1622float2(q2[u]);
+            const float2 e = __bfloat1622float2(k1[u]), f = __bfloat1622float2(k2[u]);
+            qa[u] = pack_bf16x2(a.x * c[2 * u] - bq.x * s[2 * u], a.y * c[2 * u + 1] - bq.y * s[2 * u + 1]);
+            qb[u] = pack_bf16x2(bq.x * c[2 * u] + a.x * s[2 * u], bq.y * c[2 * u + 1] + a.y * s[2 * u + 1]);
+            ka[u] = pack_bf16x2(e.x * c[2 * u] - f.x * s[2 * u], e.y * c[2 * u + 1] - f.y * s[2 * u + 1]);
+            kb[u] = pack_bf16x2(f.x * c[2 * u] + e.x * s[2 * u], f.y * c[2 * u + 1] + e.y * s[2 * u + 1]);
+        }
+        __nv_bfloat16* qo = q_out + ((long long)b * T + t) * H * D + h * D + j;
+        *reinterpret_cast<uint4*>(qo) = make_uint4(qa[0], qa[1], qa[2], qa[3]);
+        *reinterpret_cast<uint4*>(qo + half) = make_uint4(qb[0], qb[1], qb[2], qb[3]);
+        const long long co = (((long long)b * H + h) * ctx_cap + pos) * D + j;
+        *reinterpret_cast<uint4*>(cache_k + co) = make_uint4(ka[0], ka[1], ka[2], ka[3]);
+        *reinterpret_cast<uint4*>(cache_k + co + half) = make_uint4(kb[0], kb[1], kb[2], kb[3]);
+        *reinterpret_cast<uint4*>(cache_v + co) = *reinterpret_cast<const uint4*>(vp);
+        *reinterpret_cast<uint4*>(cache_v + co + half) = *reinterpret_cast<const uint4*>(vp + half);
     }
 }
 
@@ -315,9 +334,9 @@ GROMA_API int32_t groma_add_bcast(const void* a, const void* b, void* c, int64_t
 GROMA_API int32_t groma_rope_kv(const void* qkv, void* q_out, void* cache_k, void* cache_v, const float* cos_t,
                                 const float* sin_t, int32_t B, int32_t T, int32_t H, int32_t D, int32_t pos0,
                                 const int32_t* pos_ptr, int64_t ctx_cap, void* stream) {
-    if (!qkv || !q_out || !cache_k || !cache_v || !cos_t || !sin_t || (D & 1)) return GROMA_ERR_ARG;
+    if (!qkv || !q_out || !cache_k || !cache_v || !cos_t || !sin_t || (D & 15)) return GROMA_ERR_ARG;
     if (!pos_ptr && pos0 + T > ctx_cap) return GROMA_ERR_ARG;
-    rope_kv_kernel<<<grid_for((long long)B * T * H * (D / 2), 256), 256, 0, ST>>>(
+    rope_kv_kernel<<<grid_for((long long)B * T * H * (D / 16), 256), 256, 0, ST>>>(
         CBF(qkv), BF(q_out), BF(cache_k), BF(cache_v), cos_t, sin_t, B, T, H, D, pos0, pos_ptr, ctx_cap);
     return GROMA_LAUNCH_CHECK();
 }

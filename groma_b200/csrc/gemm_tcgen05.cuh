@@ -51,7 +51,10 @@ struct GemmCfg {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
     static constexpr int B_BYTES = BN * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+#ifndef GROMA_BN16_STAGES
+#define GROMA_BN16_STAGES 8
+#endif
+    static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : (BN == 16 ? GROMA_BN16_STAGES : 8));
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * (32 * 80 + 32 * 8) /*epilogue staging*/;
 };

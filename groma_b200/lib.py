@@ -12,7 +12,8 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 HEADER = ROOT.parent / "include" / "groma_b200.h"
-LIB_PATH = ROOT / "lib" / "libgroma_b200.so"
+import os as _os
+LIB_PATH = Path(_os.environ.get("GROMA_B200_LIB", str(ROOT / "lib" / "libgroma_b200.so")))   # override = A/B tuning builds only
 
 _CTYPES = {
     "int32_t": ctypes.c_int32,

@@ -38,6 +38,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tiny", action="store_true", help="debug: miniature model")
     ap.add_argument("--profile", action="store_true", help="print a per-stage CUDA-event breakdown of one step to stderr")
+    ap.add_argument("--ncu-range", action="store_true",
+                    help="wrap ONE extra step in cudaProfilerStart/Stop (use with ncu --profile-from-start off --graph-profiling node)")
     return ap.parse_args()
 
 
@@ -245,6 +247,12 @@ def main():
                 print(f"[profile] {n1:>16s}: {e0.elapsed_time(e1):9.3f} ms", file=sys.stderr)
         if rank == 0:
             print(f"[profile] {'total':>16s}: {marks[0][1].elapsed_time(marks[-1][1]):9.3f} ms", file=sys.stderr)
+    if args.ncu_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step(False)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()

@@ -76,6 +76,62 @@ __global__ void msda_kernel(const MsdaParams p) {
     p.out[bq * (long long)(p.nH * 32) + head * 32 + lane] = __float2bfloat16_rn(acc);
 }
 
+
+// ---- single-level fast path: the value slice of one (image, head) -- S x 32 bf16 = 64 KB for the 32x32 map -- is staged
+// in shared memory once (coalesced 16-byte loads) and every query of that image/head samples from it, so HBM/L2 sees the
+// algorithmic bytes only (value once, projection row once, output once) instead of 16 scattered 64-byte gathers per
+// (query, head).  grid (heads, B, q_splits); one warp per query, lane = channel.
+__global__ void __launch_bounds__(512) msda_smem_kernel(const MsdaParams p, int q_per_cta) {
+    extern __shared__ __align__(16) uint8_t sm_val[];
+    __nv_bfloat16* sv = reinterpret_cast<__nv_bfloat16*>(sm_val);   // [S][32]
+    const int head = blockIdx.x, b = blockIdx.y;
+    const int H = p.lvl_h[0], W = p.lvl_w[0];
+    // stage value[b, :, head, :]  (rows of 64 bytes at stride nH*64 bytes)
+    const __nv_bfloat16* vsrc = p.value + ((long long)b * p.S) * p.nH * 32 + head * 32;
+    for (int i = threadIdx.x; i < p.S * 4; i += blockDim.x) {
+        const int r = i >> 2, c = i & 3;
+        *reinterpret_cast<uint4*>(sv + r * 32 + c * 8) = *reinterpret_cast<const uint4*>(vsrc + (long long)r * p.nH * 32 + c * 8);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int P = p.P;
+    const int n_off = p.nH * P * 2;
+    const int q0 = blockIdx.z * q_per_cta, q1 = min(p.Q, q0 + q_per_cta);
+    for (int q = q0 + warp; q < q1; q += nw) {
+        const long long bq = (long long)b * p.Q + q;
+        const float* prow = p.proj + bq * (long long)(n_off + p.nH * P);
+        const float* off = prow + head * P * 2;
+        const float* logit = prow + n_off + head * P;
+        const float* ref = p.ref + bq * p.ref_dim;
+        float mx = -INFINITY;
+        for (int i = 0; i < P; ++i) mx = fmaxf(mx, logit[i]);
+        float den = 0.f;
+        for (int i = 0; i < P; ++i) den += __expf(logit[i] - mx);
+        const float inv_den = 1.f / den;
+        float acc = 0.f;
+        for (int k = 0; k < P; ++k) {
+            const float ox = off[k * 2], oy = off[k * 2 + 1];
+            float lx, ly;
+            if (p.ref_dim == 2) { lx = ref[0] + ox / (float)W; ly = ref[1] + oy / (float)H; }
+            else { lx = ref[0] + ox / (float)P * ref[2] * 0.5f; ly = ref[1] + oy / (float)P * ref[3] * 0.5f; }
+            const float w_attn = __expf(logit[k] - mx) * inv_den;
+            const float h_im = ly * H - 0.5f, w_im = lx * W - 0.5f;
+            if (h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W) {
+                const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+                const int h_high = h_low + 1, w_high = w_low + 1;
+                const float lh = h_im - h_low, lw = w_im - w_low, hh = 1.f - lh, hw = 1.f - lw;
+                float v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f;
+                if (h_low >= 0 && w_low >= 0) v1 = __bfloat162float(sv[(h_low * W + w_low) * 32 + lane]);
+                if (h_low >= 0 && w_high <= W - 1) v2 = __bfloat162float(sv[(h_low * W + w_high) * 32 + lane]);
+                if (h_high <= H - 1 && w_low >= 0) v3 = __bfloat162float(sv[(h_high * W + w_low) * 32 + lane]);
+                if (h_high <= H - 1 && w_high <= W - 1) v4 = __bfloat162float(sv[(h_high * W + w_high) * 32 + lane]);
+                acc += w_attn * (hh * hw * v1 + hh * lw * v2 + lh * hw * v3 + lh * lw * v4);
+            }
+        }
+        p.out[bq * (long long)(p.nH * 32) + head * 32 + lane] = __float2bfloat16_rn(acc);
+    }
+}
+
 }  // namespace gb
 using namespace gb;
 
@@ -95,6 +151,21 @@ GROMA_API int32_t groma_msda_forward(const void* value, const float* proj, const
         p.lvl_h[l] = l < n_levels ? level_hw[2 * l] : 0;
         p.lvl_w[l] = l < n_levels ? level_hw[2 * l + 1] : 0;
         p.lvl_start[l] = l < n_levels ? level_start[l] : 0;
+    }
+    if (n_levels == 1 && (long long)S * 64 <= 200 * 1024) {
+        const int smem = S * 64;
+        static int configured = 0;
+        if (smem > 48 * 1024 && smem > configured) {
+            if (cudaFuncSetAttribute(msda_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return GROMA_ERR_CUDA;
+            configured = smem;
+        }
+        // split the queries of one (image, head) over enough CTAs to fill the 148 SMs about twice
+        int qs = (2 * 148 + B * n_heads - 1) / (B * n_heads);
+        if (qs < 1) qs = 1;
+        if (qs > (Q + 63) / 64) qs = (Q + 63) / 64;
+        const int q_per_cta = (Q + qs - 1) / qs;
+        msda_smem_kernel<<<dim3(n_heads, B, qs), 512, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p, q_per_cta);
+        return GROMA_LAUNCH_CHECK();
     }
     const long long warps = (long long)B * Q * n_heads;
     const int threads = 256;

@@ -205,6 +205,41 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, causal: bool
     return out
 
 
+def _view2d(t: torch.Tensor, kind: str):
+    """Describe a [B, S, H, D] (kind 'bshd') or [B, H, S, D] (kind 'bhsd') strided view as a 2-D row-major matrix for
+    groma_attention_tc: returns (ptr tensor, rows, cols, ld, batch_rows, head_rows, head_cols)."""
+    if kind == "bshd":
+        B, S, H, D = t.shape
+        sb, ss, sh, sd = t.stride()
+        assert sd == 1 and sh == D and sb == S * ss, "expect rows = b*S + s, cols = h*D + d"
+        return t, B * S, H * D, ss, S, 0, D
+    B, H, S, D = t.shape
+    sb, sh, ss, sd = t.stride()
+    assert sd == 1
+    if ss == D and sb == H * sh:            # contiguous cache [B, H, cap, D]: rows = (b*H + h)*cap + s
+        cap = sh // D
+        return t, B * H * cap, D, D, H * cap, cap, 0
+    assert sh == D and sb == S * ss, "expect a permuted [B,S,H,D] activation view"
+    return t, B * S, H * D, ss, S, 0, D
+
+
+def attention_tc(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, causal: bool, scale: float, q_pos0: int = 0,
+                 kv_len: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, sk: Optional[int] = None) -> torch.Tensor:
+    """tcgen05 flash attention.  q [B,Sq,H,D] view; k, v [B,H,Sk,D] views (KV cache or permuted fused-qkv slices)."""
+    _bf16(q, "q"); _bf16(k, "k"); _bf16(v, "v")
+    B, Sq, H, D = q.shape
+    Sk = k.shape[2] if sk is None else sk
+    if out is None:
+        out = torch.empty((B, Sq, H * D), dtype=torch.bfloat16, device=q.device)
+    qd, kd, vd = _view2d(q, "bshd"), _view2d(k, "bhsd"), _view2d(v, "bhsd")
+    rc = _L().groma_attention_tc(_p(qd[0]), qd[1], qd[2], qd[3], qd[4], qd[6],
+                                 _p(kd[0]), kd[1], kd[2], kd[3], kd[4], kd[5], kd[6],
+                                 _p(vd[0]), vd[1], vd[2], vd[3], vd[4], vd[5], vd[6],
+                                 _p(out), out.stride(1), _p(kv_len), B, H, Sq, Sk, D, 1 if causal else 0, q_pos0, float(scale), _stream())
+    _chk(rc, "groma_attention_tc")
+    return out
+
+
 def decode_attention(q: torch.Tensor, cache_k: torch.Tensor, cache_v: torch.Tensor, kv_len: torch.Tensor, scale: float,
                      out: torch.Tensor, pdl: bool = False) -> torch.Tensor:
     """q/out [B, H*D] bf16, cache_k/v [B, H, cap, D] contiguous, kv_len int32 [B] on device."""

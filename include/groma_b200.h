@@ -75,6 +75,17 @@ int32_t groma_attention(const void* q, int64_t q_bs, int64_t q_rs, const void* k
                         int64_t o_rs, const int32_t* kv_len, int32_t B, int32_t H, int32_t Sq, int32_t Sk, int32_t D,
                         int32_t causal, int32_t q_pos0, float scale, void* stream);
 
+/* The same attention on the tcgen05 tensor cores (TMA-fed, S/O accumulators in TMEM), head_dim 64 / 128.
+ * q/k/v are 2-D bf16 row-major views [rows, cols] (row stride ld); element (b, i|j, h, d) lives at
+ *   q: row b*q_batch_rows + i,                 col h*q_head_cols + d
+ *   k: row b*k_batch_rows + h*k_head_rows + j, col h*k_head_cols + d      (v alike)
+ * -- covers the KV cache [B,H,cap,D] and fused qkv activations [B*S, 3*H*D] without copies.  o: [B*Sq, o_ld], col h*D + d. */
+int32_t groma_attention_tc(const void* q, int64_t q_rows, int64_t q_cols, int64_t q_ld, int32_t q_batch_rows, int32_t q_head_cols,
+                           const void* k, int64_t k_rows, int64_t k_cols, int64_t k_ld, int32_t k_batch_rows, int32_t k_head_rows,
+                           int32_t k_head_cols, const void* v, int64_t v_rows, int64_t v_cols, int64_t v_ld, int32_t v_batch_rows,
+                           int32_t v_head_rows, int32_t v_head_cols, void* o, int64_t o_ld, const int32_t* kv_len, int32_t B,
+                           int32_t H, int32_t Sq, int32_t Sk, int32_t D, int32_t causal, int32_t q_pos0, float scale, void* stream);
+
 /* Single-query (decode) attention over the KV cache: every cached position < kv_len[b] is visible (the all-ones mask of
  * groma/model/groma.py:376-379).  q, out [B, H*D]; cache_k/v [B, H, cap, D]; D = 128.  HBM-bound SIMT kernel. */
 int32_t groma_decode_attention(const void* q, const void* cache_k, const void* cache_v, void* out, const int32_t* kv_len,

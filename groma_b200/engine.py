@@ -35,6 +35,7 @@ class GromaEngine:
         self.stages: Dict[str, torch.Tensor] = {}
         self.keep_stages = False
         self.fused_splitk = False
+        self.use_tc_attention = True   # tcgen05 flash attention for head dims 64/128 (mma.sync kernel otherwise)
         self.fused_decode = True     # fused reduce epilogues + PDL in the decode step
         self.use_pdl = True
         self.timing_hook = None   # bench.py: list collecting (start_event, end_event, algorithmic_bytes) per swap-AB GEMM
@@ -216,8 +217,9 @@ class GromaEngine:
             o = f"vit.{i}."
             y = G.layernorm(x, w[o + "ln1.w"], w[o + "ln1.b"], cfg.vit_ln_eps)
             qkv = G.gemm(y, w[o + "qkv.w"], bias=w[o + "qkv.b"]).reshape(B, S, 3, nh, hd)
-            a = G.attention(qkv[:, :, 0], qkv[:, :, 1].permute(0, 2, 1, 3), qkv[:, :, 2].permute(0, 2, 1, 3),
-                            causal=False, scale=1.0 / math.sqrt(hd))
+            attn = G.attention_tc if (self.use_tc_attention and hd in (64, 128)) else G.attention
+            a = attn(qkv[:, :, 0], qkv[:, :, 1].permute(0, 2, 1, 3), qkv[:, :, 2].permute(0, 2, 1, 3),
+                     causal=False, scale=1.0 / math.sqrt(hd))
             xn = torch.empty_like(x) if i >= keep_from else x   # keep the hidden states that are read later intact
             G.gemm(a.reshape(B * S, H), w[o + "o.w"], bias=w[o + "o.b"], gamma=w[o + "ls1"], residual=x, out=xn)
             x = xn
@@ -435,7 +437,8 @@ class GromaEngine:
             qkv = G.gemm(y, w[o + "qkv.w"])
             kc, vc = self.kv[i, 0], self.kv[i, 1]
             G.rope_kv(qkv, q, kc, vc, self.rope_cos, self.rope_sin, B, T, nh, hd, 0)
-            a = G.attention(q.reshape(B, T, nh, hd), kc, vc, causal=True, scale=1.0 / math.sqrt(hd), kv_len=kv_len, sk=T)
+            attn = G.attention_tc if (self.use_tc_attention and hd in (64, 128)) else G.attention
+            a = attn(q.reshape(B, T, nh, hd), kc, vc, causal=True, scale=1.0 / math.sqrt(hd), kv_len=kv_len, sk=T)
             G.gemm(a.reshape(B * T, nh * hd), w[o + "o.w"], residual=x, out=x)
             y = G.rmsnorm(x, w[o + "ln2"], cfg.rms_eps)
             gu = G.gemm(y, w[o + "gu.w"], act=G.ACT_SWIGLU)

@@ -40,7 +40,10 @@ def bench_attn():
         q = torch.randn(B, S, H, D, device="cuda").bfloat16(); k = torch.randn(B, H, S, D, device="cuda").bfloat16(); v = torch.randn(B, H, S, D, device="cuda").bfloat16()
         ms = timeit(lambda: G.attention(q, k, v, causal=causal, scale=1 / math.sqrt(D)))
         fl = 4.0 * B * H * S * S * D * (0.5 if causal else 1.0)
-        print(f"attn B={B} H={H} S={S} D={D} causal={causal}: {ms:.3f} ms {fl/ms/1e9:.0f} TFLOP/s", flush=True)
+        print(f"attn(mma.sync) B={B} H={H} S={S} D={D} causal={causal}: {ms:.3f} ms {fl/ms/1e9:.0f} TFLOP/s", flush=True)
+        if D in (64, 128):
+            ms = timeit(lambda: G.attention_tc(q, k, v, causal=causal, scale=1 / math.sqrt(D)))
+            print(f"attn(tcgen05)  B={B} H={H} S={S} D={D} causal={causal}: {ms:.3f} ms {fl/ms/1e9:.0f} TFLOP/s", flush=True)
     B, H, D, ctx = 16, 32, 128, 1024
     q = torch.randn(B, 1, H, D, device="cuda").bfloat16(); k = torch.randn(B, H, ctx, D, device="cuda").bfloat16(); v = torch.randn(B, H, ctx, D, device="cuda").bfloat16()
     ms = timeit(lambda: G.attention(q, k, v, causal=True, scale=0.1, q_pos0=ctx - 1))

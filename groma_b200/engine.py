@@ -35,7 +35,10 @@ class GromaEngine:
         self.stages: Dict[str, torch.Tensor] = {}
         self.keep_stages = False
         self.fused_splitk = False
-        self.use_tc_attention = True   # tcgen05 flash attention for head dims 64/128 (mma.sync kernel otherwise)
+        # tcgen05 flash attention (attention_tcgen05.cu) is parity-green but, in its first single-Q-tile form, slower than the
+        # mma.sync kernel (145 vs 189 TFLOP/s on the prefill shape: softmax and MMA phases serialise, one CTA per SM); it
+        # stays opt-in until the two-Q-tile ping-pong version lands
+        self.use_tc_attention = False
         self.fused_decode = True     # fused reduce epilogues + PDL in the decode step
         self.use_pdl = True
         self.timing_hook = None   # bench.py: list collecting (start_event, end_event, algorithmic_bytes) per swap-AB GEMM

@@ -9,6 +9,7 @@
 // producer before touching memory, so launch latency overlaps the previous kernel (they are a few microseconds long).
 #include "ptx.cuh"
 #include "capi_common.h"
+#include <cooperative_groups.h>
 
 namespace gb {
 
@@ -69,6 +70,56 @@ __global__ void reduce_residual_rmsnorm_kernel(const float* __restrict__ ws, int
                 make_uint2(pack_bf16x2(w4.x * bf16_round(h[i][0] * rs), w4.y * bf16_round(h[i][1] * rs)),
                            pack_bf16x2(w4.z * bf16_round(h[i][2] * rs), w4.w * bf16_round(h[i][3] * rs)));
         }
+    }
+}
+
+// Cluster version: RN_CL CTAs (one thread-block cluster) per token, each owning N/RN_CL features; the per-slice sums of
+// squares are exchanged through distributed shared memory and added in rank order (deterministic), so the 13 x 16 KB of
+// split-K partials of one token are pulled by 8 SMs instead of one and the kernel stays off the decode critical path.
+constexpr int RN_CL = 8;
+__global__ void __cluster_dims__(RN_CL, 1, 1) __launch_bounds__(128)
+reduce_residual_rmsnorm_cluster_kernel(const float* __restrict__ ws, int S, int B, int N, __nv_bfloat16* __restrict__ x,
+                                       const float* __restrict__ w, __nv_bfloat16* __restrict__ y, float eps) {
+    pdl_trigger();
+    pdl_wait();
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = (int)cluster.block_rank();
+    __shared__ float red[32];
+    __shared__ float part[RN_CL];
+    const int b = blockIdx.y;
+    const int slice = N / RN_CL;                 // features per CTA (multiple of 4)
+    const int v = threadIdx.x;                   // one float4 per thread: slice <= 512
+    const int col = crank * slice + v * 4;
+    const bool act = v * 4 < slice;
+    float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f;
+    if (act) {
+        for (int s = 0; s < S; ++s) {
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(ws + ((long long)s * B + b) * N + col));
+            h0 += t.x; h1 += t.y; h2 += t.z; h3 += t.w;
+        }
+        __nv_bfloat16* xp = x + (long long)b * N + col;
+        const uint2 xr = *reinterpret_cast<const uint2*>(xp);
+        const float2 x01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xr.x));
+        const float2 x23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xr.y));
+        h0 = bf16_round(h0 + x01.x); h1 = bf16_round(h1 + x01.y); h2 = bf16_round(h2 + x23.x); h3 = bf16_round(h3 + x23.y);
+        *reinterpret_cast<uint2*>(xp) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+    }
+    const float ss_local = block_sum_f(act ? (h0 * h0 + h1 * h1 + h2 * h2 + h3 * h3) : 0.f, red);
+    if (threadIdx.x < RN_CL) {
+        float* peer = cluster.map_shared_rank(part, threadIdx.x);
+        peer[crank] = ss_local;                  // every CTA publishes its slice sum to all peers
+    }
+    cluster.sync();
+    float ss = 0.f;
+#pragma unroll
+    for (int r = 0; r < RN_CL; ++r) ss += part[r];
+    const float rs = rsqrtf(ss / N + eps);
+    if (act) {
+        const float4 w4 = *reinterpret_cast<const float4*>(w + col);
+        *reinterpret_cast<uint2*>(y + (long long)b * N + col) =
+            make_uint2(pack_bf16x2(w4.x * bf16_round(h0 * rs), w4.y * bf16_round(h1 * rs)),
+                       pack_bf16x2(w4.z * bf16_round(h2 * rs), w4.w * bf16_round(h3 * rs)));
     }
 }
 
@@ -149,6 +200,8 @@ GROMA_API int32_t groma_decode_reduce_norm(const float* ws, int32_t splits, int3
     const int nvec = N >> 2;
     auto X = reinterpret_cast<__nv_bfloat16*>(x);
     auto Y = reinterpret_cast<__nv_bfloat16*>(y);
+    if (N % (RN_CL * 4) == 0 && N / RN_CL <= 512 && N >= 1024)
+        return launch_pdl(reduce_residual_rmsnorm_cluster_kernel, dim3(RN_CL, B), dim3(128), st, pdl, ws, splits, B, N, X, w, Y, eps);
     if (nvec <= 1024) return launch_pdl(reduce_residual_rmsnorm_kernel<1>, dim3(B), dim3(((nvec + 31) / 32) * 32), st, pdl, ws, splits, B, N, X, w, Y, eps);
     if (nvec <= 4096) return launch_pdl(reduce_residual_rmsnorm_kernel<4>, dim3(B), dim3(1024), st, pdl, ws, splits, B, N, X, w, Y, eps);
     return GROMA_ERR_UNSUPPORTED;

@@ -201,7 +201,8 @@ GROMA_API int32_t groma_msda_forward(const void* value, const float* proj, const
             configured = smem;
         }
         // split the queries of one (image, head) over enough CTAs to fill the 148 SMs about twice
-        int qs = (2 * 148 + B * n_heads - 1) / (B * n_heads);
+        // 64 KB of shared memory per CTA -> 3 CTAs resident per SM: keep the whole grid in ONE wave
+        int qs = (3 * 148) / (B * n_heads);
         if (qs < 1) qs = 1;
         if (qs > (Q + 63) / 64) qs = (Q + 63) / 64;
         const int q_per_cta = (Q + qs - 1) / qs;

@@ -45,12 +45,35 @@ static int num_sms() {
     return g_num_sms;
 }
 
+// 2-CTA (cta_group::2) launch: clusters of two CTAs, each cluster owns 256 x 256 output tiles
+static int launch_gemm_2cta(const GemmParams& p, cudaStream_t stream) {
+    using Cfg = GemmCfg<256, 2>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
+            return GROMA_ERR_CUDA;
+        attr_set = true;
+    }
+    const int m_tiles = (p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+    const int n_tiles = (p.N + 255) / 256;
+    const int work = m_tiles * n_tiles;
+    int clusters = num_sms() / 2;
+    if (work < clusters) clusters = work;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * 2); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<256, 2>, p) == cudaSuccess ? GROMA_OK : GROMA_ERR_CUDA;
+}
+
 template <int BN>
 static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return GROMA_ERR_CUDA;
         attr_set = true;
@@ -66,9 +89,9 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN>, p) == cudaSuccess ? GROMA_OK : GROMA_ERR_CUDA;
+        return cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, 1>, p) == cudaSuccess ? GROMA_OK : GROMA_ERR_CUDA;
     }
-    gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+    gemm_bf16_tcgen05_kernel<BN, 1><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? GROMA_OK : GROMA_ERR_CUDA;
 }
 
@@ -161,7 +184,7 @@ GROMA_API int32_t groma_gemm_bf16(const void* A, int64_t a_rows, int64_t lda, co
     GemmParams p;
     int rc = make_tma_2d(&p.tma_a, A, (uint64_t)a_rows, (flags & GF_A_TILED) ? (uint64_t)GEMM_BK : (uint64_t)K, (uint64_t)lda, GEMM_BM);
     if (rc) return rc;
-    rc = make_tma_2d(&p.tma_b, B, (uint64_t)b_rows, (uint64_t)K * num_taps, (uint64_t)ldb, (uint32_t)bn);
+    rc = make_tma_2d(&p.tma_b, B, (uint64_t)b_rows, (uint64_t)K * num_taps, (uint64_t)ldb, bn == 512 ? 128u : (uint32_t)bn);
     if (rc) return rc;
     p.M = M; p.N = N; p.K = K; p.num_taps = num_taps;
     for (int i = 0; i < GEMM_MAX_TAPS; ++i) p.a_row_off[i] = (a_row_off && i < num_taps) ? a_row_off[i] : 0;
@@ -170,6 +193,10 @@ GROMA_API int32_t groma_gemm_bf16(const void* A, int64_t a_rows, int64_t lda, co
     p.bias = bias; p.gamma = gamma; p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
     p.ws = ws; p.conv_hp = conv_hp; p.conv_wp = conv_wp; p.tile_counters = tile_counters;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (bn == 512) {   // block_n = 512 selects the 2-CTA (256 x 256 per cluster) kernel
+        if (split_k != 1 || (flags & (GF_PARTIAL | GF_PDL | GF_A_TILED))) return GROMA_ERR_ARG;
+        return launch_gemm_2cta(p, st);
+    }
     switch (bn) {
         case 16: return launch_gemm<16>(p, st);
         case 32: return launch_gemm<32>(p, st);

@@ -46,15 +46,16 @@ struct GemmParams {
     int* tile_counters;    // GF_PARTIAL + non-null: the CTA that completes a tile's last split reduces ws and runs the epilogue
 };
 
-template <int BN>
+template <int BN, int CG = 1>
 struct GemmCfg {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-    static constexpr int B_BYTES = BN * GEMM_BK * 2;
+    static constexpr int B_ROWS = BN / CG;             // cta_group::2: each CTA of the pair stages half of the B tile
+    static constexpr int B_BYTES = B_ROWS * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 #ifndef GROMA_BN16_STAGES
 #define GROMA_BN16_STAGES 8
 #endif
-    static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : (BN == 16 ? GROMA_BN16_STAGES : 8));
+    static constexpr int STAGES = (CG == 2) ? 6 : ((BN >= 256) ? 4 : (BN >= 128 ? 6 : (BN == 16 ? GROMA_BN16_STAGES : 8)));
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * (32 * 80 + 32 * 8) /*epilogue staging*/;
 };
@@ -79,9 +80,14 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
-template <int BN>
+// CG = 1: one CTA per 128 x BN tile (cta_group::1).  CG = 2: a 2-CTA cluster computes a 256 x BN tile with
+// tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows of A and HALF of the B tile, the pair's tensor cores read
+// both halves, so shared-memory fill + operand-read traffic per SM drops from ~192 to ~128 B/clk (the limiter of the
+// single-CTA 128x256 tile) and the ring deepens from 4 to 6 stages.  Leader CTA (rank 0) issues the MMAs; barriers:
+// full (leader, one arrive per CTA + all TMA bytes), empty / tmem_full (both CTAs, multicast commit), tmem_empty (leader).
+template <int BN, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, CG>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -97,7 +103,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+    const int crank = (CG == 2) ? (int)cluster_ctarank() : 0;     // rank inside the CTA pair
+    const int wid0 = blockIdx.x / CG, wstride = gridDim.x / CG;     // work is distributed over clusters
+    const int m_tiles = (p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG);  // cluster-level m blocks (128*CG rows)
     const int n_tiles = (p.N + BN - 1) / BN;
     const int kb_per_tap = (p.K + GEMM_BK - 1) / GEMM_BK;
     const int total_iters = kb_per_tap * p.num_taps;
@@ -111,20 +119,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
     if (warp == 1) {
         if (lane == 0) {
             for (int i = 0; i < STAGES; ++i) {
-                mbar_init(&full_bar[i], 1);
+                mbar_init(&full_bar[i], CG);   // one arrive per CTA of the pair (+ the TMA bytes of both)
                 mbar_init(&empty_bar[i], 1);
             }
             for (int i = 0; i < 2; ++i) {
                 mbar_init(&tfull_bar[i], 1);
-                mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+                mbar_init(&tempty_bar[i], 4 * CG);  // one arrive per epilogue warp (of both CTAs)
             }
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc<Cfg::TMEM_COLS>(tmem_holder);
+        if constexpr (CG == 2) tmem_alloc_2cta<Cfg::TMEM_COLS>(tmem_holder);
+        else tmem_alloc<Cfg::TMEM_COLS>(tmem_holder);
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
@@ -135,16 +144,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
             uint32_t phase = 0;
             const bool a_tiled = (p.flags & GF_A_TILED) != 0;
             // work iterator over this CTA's (work item, k-iteration) pairs
-            int w = blockIdx.x, it = 0, it1 = 0, m_blk = 0, n_blk = 0;
+            int w = wid0, it = 0, it1 = 0, m_blk = 0, n_blk = 0;
             auto load_work = [&]() {
                 while (w < num_work) {
                     const int split = w % p.split_k;
                     const int tile = w / p.split_k;
                     tile_coords(tile, m_tiles, n_tiles, m_blk, n_blk);
+                    m_blk = m_blk * CG + crank;           // this CTA's 128-row block
                     it = split * iters_per_split;
                     it1 = min(total_iters, it + iters_per_split);
                     if (it < it1) return true;
-                    w += gridDim.x;   // empty split: nothing to load
+                    w += wstride;   // empty split: nothing to load
                 }
                 return false;
             };
@@ -153,7 +163,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
                 else { c0 = kb * GEMM_BK; c1 = m_blk * GEMM_BM + p.a_row_off[tap]; }
             };
             bool have = load_work();
-            if (p.flags & GF_PDL) {
+            if ((CG == 1) && (p.flags & GF_PDL)) {
                 // The A operand (weights) does not depend on the previous kernel: fill the ring with A tiles first, only then
                 // wait for the producer of B (activations).  Hides launch + prologue + first-byte latency of every decode GEMM.
                 int bc0[STAGES], bc1[STAGES];
@@ -167,7 +177,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
                     bc0[issued] = tap * p.K + kb * GEMM_BK;
                     bc1[issued] = n_blk * BN;
                     ++issued;
-                    if (++it >= it1) { w += gridDim.x; have = load_work(); }
+                    if (++it >= it1) { w += wstride; have = load_work(); }
                 }
                 asm volatile("griddepcontrol.wait;" ::: "memory");
                 for (int i = 0; i < issued; ++i)
@@ -181,22 +191,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
                 uint8_t* sb = sa + Cfg::A_BYTES;
                 int c0, c1;
                 a_coords(tap, kb, c0, c1);
-                mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                tma_load_2d(sa, &p.tma_a, &full_bar[stage], c0, c1);
-                tma_load_2d(sb, &p.tma_b, &full_bar[stage], tap * p.K + kb * GEMM_BK, n_blk * BN);
+                if constexpr (CG == 2) {
+                    // both CTAs credit the LEADER's full barrier: the leader arms it with the bytes of the whole pair
+                    if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                    else mbar_arrive_cta(&full_bar[stage], 0);
+                    tma_load_2d_2sm(sa, &p.tma_a, &full_bar[stage], c0, c1);
+                    tma_load_2d_2sm(sb, &p.tma_b, &full_bar[stage], tap * p.K + kb * GEMM_BK, n_blk * BN + crank * Cfg::B_ROWS);
+                } else {
+                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    tma_load_2d(sa, &p.tma_a, &full_bar[stage], c0, c1);
+                    tma_load_2d(sb, &p.tma_b, &full_bar[stage], tap * p.K + kb * GEMM_BK, n_blk * BN);
+                }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                if (++it >= it1) { w += gridDim.x; have = load_work(); }
+                if (++it >= it1) { w += wstride; have = load_work(); }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN);
+        if (lane == 0 && crank == 0) {          // cta_group::2: only the leader CTA issues MMAs
+            constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM * CG, BN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+            for (int w = wid0; w < num_work; w += wstride) {
                 const int split = w % p.split_k;
                 const int it0 = split * iters_per_split;
                 const int it1 = min(total_iters, it0 + iters_per_split);
@@ -213,12 +231,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
 #pragma unroll
                     for (int k = 0; k < GEMM_BK / 16; ++k) {
                         // advancing 16 bf16 (=32 B) along K inside the swizzle atom: +2 in 16-byte units
-                        umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it > it0 || k > 0) ? 1u : 0u);
+                        if constexpr (CG == 2) umma_bf16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (it > it0 || k > 0) ? 1u : 0u);
+                        else umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it > it0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);
+                    if constexpr (CG == 2) umma_commit_2cta(&empty_bar[stage], 0x3); else umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull_bar[acc]);
+                if constexpr (CG == 2) umma_commit_2cta(&tfull_bar[acc], 0x3); else umma_commit(&tfull_bar[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -230,11 +249,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
         const bool out_f32 = (p.flags & GF_OUT_F32) != 0;
         const bool bias_m = (p.flags & GF_BIAS_ALONG_M) != 0;
         const bool partial = (p.flags & GF_PARTIAL) != 0;
-        for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        for (int w = wid0; w < num_work; w += wstride) {
             const int split = w % p.split_k;
             const int tile = w / p.split_k;
             int m_blk, n_blk;
             tile_coords(tile, m_tiles, n_tiles, m_blk, n_blk);
+            m_blk = m_blk * CG + crank;
             const int it0 = split * iters_per_split;
             const bool has_work = it0 < total_iters;  // an empty split contributes zeros
             mbar_wait(&tfull_bar[acc], acc_phase);
@@ -480,19 +500,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 continue;
             }
-            // release this accumulator stage back to the MMA warp
+            // release this accumulator stage back to the MMA warp (of the leader CTA)
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) { if constexpr (CG == 2) mbar_arrive_cta(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]); }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // pair: no CTA may exit while its peer still signals its barriers
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+        if constexpr (CG == 2) tmem_dealloc_2cta<Cfg::TMEM_COLS>(tmem_base);
+        else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
     }
 }
 

@@ -35,6 +35,7 @@ class GromaEngine:
         self.stages: Dict[str, torch.Tensor] = {}
         self.keep_stages = False
         self.fused_splitk = False
+        self.use_2cta = True           # cta_group::2 GEMM for the large prefill projections and 3x3 convs
         # tcgen05 flash attention (attention_tcgen05.cu) is parity-green but, in its first single-Q-tile form, slower than the
         # mma.sync kernel (145 vs 189 TFLOP/s on the prefill shape: softmax and MMA phases serialise, one CTA per SM); it
         # stays opt-in until the two-Q-tile ping-pong version lands
@@ -383,7 +384,7 @@ class GromaEngine:
             for l in range(3):
                 s = sizes[l]
                 xin = G.fuse_shuffle(xs[l], xs[min(l + 1, 2)], xs[max(l - 1, 0)])
-                y = G.conv3x3_flat(xin.reshape(-1, C), w[f"fuse.{k}.w"], B, s + 2, s + 2)
+                y = G.conv3x3_flat(xin.reshape(-1, C), w[f"fuse.{k}.w"], B, s + 2, s + 2, block_n=512 if (self.use_2cta and C >= 512) else 0)
                 new.append(G.groupnorm_relu(y, w[f"fuse.{k}.gn.w"], w[f"fuse.{k}.gn.b"], cfg.gn_groups, 1e-5, B, out=y).reshape(B, s, s, C))
             xs = new
         if self.keep_stages:
@@ -399,7 +400,8 @@ class GromaEngine:
         rbuf = torch.empty((3, K, rp, rp, C), dtype=torch.bfloat16, device=self.dev)
         for l in range(3):
             G.roi_align(xs[l], rois, ro, (8, 4, 2)[l] / 14.0, cfg.roi_sampling, True, pad=True, out=rbuf[l])
-        fused = G.conv3x3_flat(rbuf.reshape(-1, C), w["pconv.w"], K, rp, rp, bias=w["pconv.b"], act=G.ACT_RELU)  # [K*ro*ro, C]
+        fused = G.conv3x3_flat(rbuf.reshape(-1, C), w["pconv.w"], K, rp, rp, bias=w["pconv.b"], act=G.ACT_RELU,
+                               block_n=512 if (self.use_2cta and C >= 512 and K * rp * rp >= 2048) else 0)  # [K*ro*ro, C]
         self._stage("roi_fused", fused.reshape(K, ro, ro, C))
         flat_in = fused.reshape(K, ro * ro * C)
         kt = flat_in.shape[1]
@@ -434,18 +436,21 @@ class GromaEngine:
         cfg, w = self.cfg, self.w
         nh, hd = cfg.llm_heads, cfg.head_dim
         q = torch.empty((B * T, nh * hd), dtype=torch.bfloat16, device=self.dev)
+        # cta_group::2 (256x256 tiles per CTA pair) for the big projections: +4..8 % over the single-CTA tile; the 22016-wide
+        # gate/up projection measured 3 % slower with it and keeps the 128x256 tile
+        bn2 = 512 if (self.use_2cta and B * T >= 2048 and cfg.llm_hidden >= 2048) else 0
         for i in range(cfg.llm_layers):
             o = f"llm.{i}."
             y = G.rmsnorm(x, w[o + "ln1"], cfg.rms_eps)
-            qkv = G.gemm(y, w[o + "qkv.w"])
+            qkv = G.gemm(y, w[o + "qkv.w"], block_n=bn2)
             kc, vc = self.kv[i, 0], self.kv[i, 1]
             G.rope_kv(qkv, q, kc, vc, self.rope_cos, self.rope_sin, B, T, nh, hd, 0)
             attn = G.attention_tc if (self.use_tc_attention and hd in (64, 128)) else G.attention
             a = attn(q.reshape(B, T, nh, hd), kc, vc, causal=True, scale=1.0 / math.sqrt(hd), kv_len=kv_len, sk=T)
-            G.gemm(a.reshape(B * T, nh * hd), w[o + "o.w"], residual=x, out=x)
+            G.gemm(a.reshape(B * T, nh * hd), w[o + "o.w"], residual=x, out=x, block_n=bn2)
             y = G.rmsnorm(x, w[o + "ln2"], cfg.rms_eps)
             gu = G.gemm(y, w[o + "gu.w"], act=G.ACT_SWIGLU)
-            G.gemm(gu, w[o + "down.w"], residual=x, out=x)
+            G.gemm(gu, w[o + "down.w"], residual=x, out=x, block_n=bn2)
         self.past = T
         if last_only:
             x = x.reshape(B, T, -1)[:, -1].contiguous()

@@ -253,8 +253,14 @@ GROMA_API int32_t groma_attention(const void* q, int64_t q_bs, int64_t q_rs, con
 // Semantics = groma/model/groma.py:376-379 + eager LLaMA attention: every cached position < kv_len[b] is visible.
 namespace gb {
 
-constexpr int DEC_WARPS = 2;   // 2 warps/CTA, 2 CTAs (one cluster) per (batch, head): 2*B*H CTAs all resident in one wave
-constexpr int DEC_SPLIT = 2;                   // keys are split over the CTAs of a cluster; partials merge through DSMEM
+#ifndef GROMA_DEC_WARPS
+#define GROMA_DEC_WARPS 2
+#endif
+#ifndef GROMA_DEC_SPLIT
+#define GROMA_DEC_SPLIT 2
+#endif
+constexpr int DEC_WARPS = GROMA_DEC_WARPS;   // 2 warps/CTA, 2 CTAs (one cluster) per (batch, head): 2*B*H CTAs all resident in one wave
+constexpr int DEC_SPLIT = GROMA_DEC_SPLIT;                   // keys are split over the CTAs of a cluster; partials merge through DSMEM
 
 // streaming 16-byte load that does not allocate in L1 (the KV cache is read once per step)
 __device__ __forceinline__ uint4 ld_nc_u4(const __nv_bfloat16* p) {
@@ -403,6 +409,172 @@ __global__ void __cluster_dims__(DEC_SPLIT, 1, 1) __launch_bounds__(DEC_WARPS * 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Same decode attention with the K/V stream staged by the TMA engine: per CTA one producer lane issues 1-D bulk copies of
+// DT_KEYS consecutive K rows and V rows (contiguous in the [B,H,cap,D] cache) into a DT_STAGES-deep shared-memory ring,
+// the DEC_WARPS consumer warps run the identical per-key arithmetic out of shared memory (same key->half-warp assignment
+// and the same groups of 4 keys per online-softmax update as decode_attention_kernel<128,4>, so results are bit-identical).
+// Bytes in flight no longer depend on registers/occupancy: 8 resident CTAs x 24 KB per SM.
+constexpr int DT_UNROLL = 4;
+constexpr int DT_KEYS = DEC_WARPS * 2 * DT_UNROLL;   // keys per stage (16)
+#ifndef GROMA_DT_STAGES
+#define GROMA_DT_STAGES 2
+#endif
+constexpr int DT_STAGES = GROMA_DT_STAGES;
+
+template <int D>
+__global__ void __cluster_dims__(DEC_SPLIT, 1, 1) __launch_bounds__((DEC_WARPS + 1) * 32) decode_attention_tma_kernel(
+    const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc, const __nv_bfloat16* __restrict__ vc,
+    __nv_bfloat16* __restrict__ out, const int* __restrict__ kv_len, int H, long long cap, float scale_log2) {
+    static_assert(D == 128, "16 lanes x 8 dims");
+    __shared__ __align__(128) __nv_bfloat16 ring[DT_STAGES][2][DT_KEYS * D];
+    __shared__ __align__(8) uint64_t full_bar[DT_STAGES], empty_bar[DT_STAGES];
+    __shared__ float sm_m[DEC_WARPS * 2], sm_l[DEC_WARPS * 2], sm_acc[DEC_WARPS * 2][D];
+    __shared__ float peer_m[DEC_SPLIT], peer_l[DEC_SPLIT], peer_acc[DEC_SPLIT][D];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < DT_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], DEC_WARPS); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = (int)cluster.block_rank();
+    const int h = blockIdx.x / DEC_SPLIT, b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane >> 4, l = lane & 15;
+    const int n_all = kv_len[b];
+    const int per = (n_all + DEC_SPLIT - 1) / DEC_SPLIT;
+    const int k_begin = min(crank * per, n_all);
+    const int n = min(n_all, k_begin + per) - k_begin;
+    const int nchunks = (n + DT_KEYS - 1) / DT_KEYS;
+    const __nv_bfloat16* kb = kc + (((long long)b * H + h) * cap + k_begin) * D;
+    const __nv_bfloat16* vb = vc + (((long long)b * H + h) * cap + k_begin) * D;
+    if (warp == DEC_WARPS) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int c = 0; c < nchunks; ++c) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                const int keys = min(DT_KEYS, n - c * DT_KEYS);
+                const uint32_t bytes = (uint32_t)keys * D * 2;
+                mbar_expect_tx(&full_bar[stage], 2 * bytes);
+                bulk_load_1d(&ring[stage][0][0], kb + (long long)c * DT_KEYS * D, bytes, &full_bar[stage]);
+                bulk_load_1d(&ring[stage][1][0], vb + (long long)c * DT_KEYS * D, bytes, &full_bar[stage]);
+                if (++stage == DT_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        float qf[8];
+        {
+            const uint4 qv = *reinterpret_cast<const uint4*>(q + ((long long)b * H + h) * D + l * 8);
+            const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&qv);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float2 f = __bfloat1622float2(q2[t]);
+                qf[2 * t] = f.x * scale_log2;
+                qf[2 * t + 1] = f.y * scale_log2;
+            }
+        }
+        float m = -INFINITY, lsum = 0.f, acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        constexpr int STEP = DEC_WARPS * 2;
+        const int slot = warp * 2 + grp;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int c = 0; c < nchunks; ++c) {
+            mbar_wait(&full_bar[stage], phase);
+            const __nv_bfloat16* ks = &ring[stage][0][0];
+            const __nv_bfloat16* vs = &ring[stage][1][0];
+            const int left = n - c * DT_KEYS;   // valid keys in this stage
+            float s[DT_UNROLL];
+            uint4 vv[DT_UNROLL];
+#pragma unroll
+            for (int u = 0; u < DT_UNROLL; ++u) {
+                const int j = slot + u * STEP;
+                const bool ok = j < left;
+                const uint4 kk = ok ? *reinterpret_cast<const uint4*>(ks + j * D + l * 8) : make_uint4(0, 0, 0, 0);
+                vv[u] = ok ? *reinterpret_cast<const uint4*>(vs + j * D + l * 8) : make_uint4(0, 0, 0, 0);
+                const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kk);
+                float d = 0.f;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float2 f = __bfloat1622float2(k2[t]);
+                    d += f.x * qf[2 * t] + f.y * qf[2 * t + 1];
+                }
+                d += __shfl_xor_sync(0xffffffffu, d, 8);
+                d += __shfl_xor_sync(0xffffffffu, d, 4);
+                d += __shfl_xor_sync(0xffffffffu, d, 2);
+                d += __shfl_xor_sync(0xffffffffu, d, 1);
+                s[u] = ok ? d : -INFINITY;
+            }
+            float mn = m;
+#pragma unroll
+            for (int u = 0; u < DT_UNROLL; ++u) mn = fmaxf(mn, s[u]);
+            const float mref = (mn == -INFINITY) ? 0.f : mn;
+            const float corr = exp2f(m - mref);
+            m = mn;
+            lsum *= corr;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) acc[t] *= corr;
+#pragma unroll
+            for (int u = 0; u < DT_UNROLL; ++u) {
+                const float p = exp2f(s[u] - mref);
+                lsum += p;
+                const float pr = bf16_round(p);
+                const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vv[u]);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float2 f = __bfloat1622float2(v2[t]);
+                    acc[2 * t] += pr * f.x;
+                    acc[2 * t + 1] += pr * f.y;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            if (++stage == DT_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (l == 0) { sm_m[slot] = m; sm_l[slot] = lsum; }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) sm_acc[slot][l * 8 + t] = acc[t];
+    }
+    __syncthreads();
+    float* r_m = cluster.map_shared_rank(peer_m, 0);
+    float* r_l = cluster.map_shared_rank(peer_l, 0);
+    float* r_acc = cluster.map_shared_rank(&peer_acc[0][0], 0);
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < DEC_WARPS * 2; ++w) M = fmaxf(M, sm_m[w]);
+        float num = 0.f, den = 0.f;
+#pragma unroll
+        for (int w = 0; w < DEC_WARPS * 2; ++w) {
+            const float c = (sm_m[w] == -INFINITY) ? 0.f : exp2f(sm_m[w] - M);
+            num += c * sm_acc[w][d];
+            den += c * sm_l[w];
+        }
+        r_acc[crank * D + d] = num;
+        if (d == 0) { r_m[crank] = M; r_l[crank] = den; }
+    }
+    cluster.sync();
+    if (crank == 0) {
+        for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            float M = -INFINITY;
+#pragma unroll
+            for (int r = 0; r < DEC_SPLIT; ++r) M = fmaxf(M, peer_m[r]);
+            float num = 0.f, den = 0.f;
+#pragma unroll
+            for (int r = 0; r < DEC_SPLIT; ++r) {
+                const float c = (peer_m[r] == -INFINITY) ? 0.f : exp2f(peer_m[r] - M);
+                num += c * peer_acc[r][d];
+                den += c * peer_l[r];
+            }
+            out[((long long)b * H + h) * D + d] = __float2bfloat16_rn(den > 0.f ? num / den : 0.f);
+        }
+    }
+}
+
 }  // namespace gb
 
 GROMA_API int32_t groma_decode_attention(const void* q, const void* cache_k, const void* cache_v, void* out,
@@ -425,6 +597,13 @@ GROMA_API int32_t groma_decode_attention(const void* q, const void* cache_k, con
     auto O = reinterpret_cast<__nv_bfloat16*>(out);
     const float sl2 = scale * 1.4426950408889634f;
     cudaError_t e;
+    static int use_tma = -1;   // default: K/V staged through the TMA ring (decode_attention_tma_kernel); GROMA_DEC_ATTN_TMA=0 = LDG kernel
+    if (use_tma < 0) { const char* ev = getenv("GROMA_DEC_ATTN_TMA"); use_tma = ev ? atoi(ev) : 1; }
+    if (use_tma) {
+        cfg.blockDim = dim3((gb::DEC_WARPS + 1) * 32);
+        e = cudaLaunchKernelEx(&cfg, gb::decode_attention_tma_kernel<128>, Q, K, V, O, kv_len, (int)H, (long long)cap, sl2);
+        return e == cudaSuccess ? GROMA_OK : GROMA_ERR_CUDA;
+    }
     if (unroll == 8) e = cudaLaunchKernelEx(&cfg, gb::decode_attention_kernel<128, 8>, Q, K, V, O, kv_len, (int)H, (long long)cap, sl2);
     else if (unroll == 6) e = cudaLaunchKernelEx(&cfg, gb::decode_attention_kernel<128, 6>, Q, K, V, O, kv_len, (int)H, (long long)cap, sl2);
     else if (unroll == 2) e = cudaLaunchKernelEx(&cfg, gb::decode_attention_kernel<128, 2>, Q, K, V, O, kv_len, (int)H, (long long)cap, sl2);

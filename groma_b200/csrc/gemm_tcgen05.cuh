@@ -44,6 +44,7 @@ struct GemmParams {
     float* ws;             // fp32 partials [split][M][N] when GF_PARTIAL
     int conv_hp, conv_wp;  // padded map dims for GF_CONV_ROWS
     int* tile_counters;    // GF_PARTIAL + non-null: the CTA that completes a tile's last split reduces ws and runs the epilogue
+    int early_trigger;     // GF_PDL: release the dependent grid at kernel start (it parks at its own griddepcontrol.wait)
 };
 
 template <int BN, int CG = 1>
@@ -53,7 +54,7 @@ struct GemmCfg {
     static constexpr int B_BYTES = B_ROWS * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 #ifndef GROMA_BN16_STAGES
-#define GROMA_BN16_STAGES 8
+#define GROMA_BN16_STAGES 4
 #endif
     static constexpr int STAGES = (CG == 2) ? 6 : ((BN >= 256) ? 4 : (BN >= 128 ? 6 : (BN == 16 ? GROMA_BN16_STAGES : 8)));
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
@@ -136,6 +137,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
     if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    // Dependents only touch this grid's results after their own griddepcontrol.wait (= this grid complete and flushed), so
+    // releasing them now is safe; it lets the next kernels become resident and the next GEMM stream its weights early.
+    if (p.early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
         // ===================== TMA producer =====================

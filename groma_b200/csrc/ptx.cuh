@@ -57,6 +57,13 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* d) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(d)) : "memory");
 }
 // 2D tiled load: coordinates are (inner, outer) element indices; signed, OOB zero-filled.
+// 1-D bulk copy global -> shared (16-byte aligned address/size), completion counted on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gptr, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gptr), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* d, uint64_t* bar, int32_t c0,
                                             int32_t c1) {
     asm volatile(

@@ -9,6 +9,7 @@ replaces are cited at the methods (paths relative to the FoundationVision/Groma 
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -35,6 +36,8 @@ class GromaEngine:
         self.stages: Dict[str, torch.Tensor] = {}
         self.keep_stages = False
         self.fused_splitk = False
+        self.decode_tiled = os.environ.get("GROMA_DECODE_TILED", "0") == "1"   # decode GEMMs stream a tile-major weight copy (+13 GB)
+        self._wt: Dict[str, torch.Tensor] = {}
         self.use_2cta = True           # cta_group::2 GEMM for the large prefill projections and 3x3 convs
         # tcgen05 flash attention (attention_tcgen05.cu) is parity-green but, in its first single-Q-tile form, slower than the
         # mma.sync kernel (145 vs 189 TFLOP/s on the prefill shape: softmax and MMA phases serialise, one CTA per SM); it
@@ -481,10 +484,13 @@ class GromaEngine:
         return d
 
     def _decode_splits(self):
-        """Split-K factors of the five decode GEMMs: (weight row-tiles of 128) x split should fill whole waves of the 148
-        SMs; e.g. gate/up has 172 tiles -> 1 split wastes 42% of the second wave, 6 splits give 1032 items = 6.97 waves."""
+        """Split-K factors of the five decode GEMMs: (weight row-tiles of 128) x split should fill whole waves of the 296
+        CTA slots (2 per SM); e.g. gate/up has 172 tiles -> 1 split leaves 42% of the slots idle, 5 splits give 860 items =
+        2.9 waves."""
         if getattr(self, "_splits", None) is None:
             cfg = self.cfg
+
+            ncta = 148 * max(1, int(os.environ.get("GROMA_GEMM_CTAS_PER_SM", "2")))   # the BN=16 kernel runs 2 CTAs per SM
 
             def pick(n_rows, k):
                 tiles = (n_rows + 127) // 128
@@ -496,8 +502,8 @@ class GromaEngine:
                     per = (kb + s - 1) // s
                     s_eff = (kb + per - 1) // per          # splits that actually receive work
                     items = tiles * s_eff
-                    waves = (items + 147) // 148
-                    eff = (tiles * kb) / (waves * 148 * per) - 0.004 * s   # small penalty: more fp32 partials to reduce
+                    waves = (items + ncta - 1) // ncta
+                    eff = (tiles * kb) / (waves * ncta * per) - 0.004 * s   # small penalty: more fp32 partials to reduce
                     if eff > best_eff:
                         best, best_eff = s, eff
                 return best
@@ -527,6 +533,13 @@ class GromaEngine:
             G.splitk_reduce(ws, out, act=act, residual=residual, bias_along_m=True, ld_m=1, ld_n=n_out)
         return out
 
+    def _tiled(self, wname: str) -> torch.Tensor:
+        """Tile-major copy of a decode weight (every 128x64 TMA box = one contiguous 16 KB run of HBM); built on first use."""
+        t = self._wt.get(wname)
+        if t is None:
+            t = self._wt[wname] = G.tile_weight(self.w[wname])
+        return t
+
     def decode_step(self, B: int) -> torch.Tensor:
         """One greedy decode step for the whole batch (groma.py:376-402 + HF greedy argmax): reads d['ids'], appends K/V at
         *pos, attends to all kv_len[b] cached positions (all-ones mask, T7), writes next ids back to d['ids'].
@@ -550,7 +563,10 @@ class GromaEngine:
             if self.timing_hook is not None:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
-            G.gemm_swap_ab(inp, W, ws, split_k=split, pdl=pdl, transposed=True)
+            if self.decode_tiled:
+                G.gemm_swap_ab(inp, self._tiled(wname), ws, split_k=split, pdl=pdl, transposed=True, tiled=True, n_rows=W.shape[0])
+            else:
+                G.gemm_swap_ab(inp, W, ws, split_k=split, pdl=pdl, transposed=True)
             if self.timing_hook is not None:
                 ev1.record()
                 self.timing_hook.append((ev0, ev1, W.numel() * 2 + inp.numel() * 2 + ws.numel() * 4))

@@ -525,3 +525,28 @@ def decode_reduce_rope_kv(ws: torch.Tensor, q_out: torch.Tensor, cache_k: torch.
     assert N == 3 * H * D
     _chk(_L().groma_decode_reduce_rope_kv(_p(ws), S, B, H, D, _p(q_out), _p(cache_k), _p(cache_v), _p(cos_t), _p(sin_t),
                                           _p(pos_ptr), cache_k.shape[2], 1 if pdl else 0, _stream()), "groma_decode_reduce_rope_kv")
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# image preprocessing
+PREPROCESS_KMAX = 64
+
+
+def preprocess_image(img: torch.Tensor, lut: torch.Tensor, out_size: int, out_f32: Optional[torch.Tensor] = None,
+                     out_u8: Optional[torch.Tensor] = None) -> None:
+    """Pillow-exact bicubic resize of one uint8 HWC RGB cuda image to out_size^2, then the byte->float32 table `lut` [3,256]
+    (rescale + normalize) into out_f32 [3,S,S]; out_u8 [S,S,3] receives the resized bytes.  See include/groma_b200.h."""
+    if img.dtype != torch.uint8 or img.dim() != 3 or img.shape[2] != 3 or not img.is_cuda or img.stride(2) != 1 or img.stride(1) != 3:
+        raise ValueError("img must be a cuda uint8 [H, W, 3] tensor with packed RGB pixels")
+    H, W = int(img.shape[0]), int(img.shape[1])
+    tmp = torch.empty((H, out_size, 3), dtype=torch.uint8, device=img.device)
+    coef = torch.empty((2 * out_size * (2 + PREPROCESS_KMAX),), dtype=torch.int32, device=img.device)
+    if out_f32 is not None and (out_f32.dtype != torch.float32 or not out_f32.is_contiguous() or out_f32.numel() != 3 * out_size * out_size):
+        raise ValueError("out_f32 must be contiguous float32 [3, S, S]")
+    if out_u8 is not None and (out_u8.dtype != torch.uint8 or not out_u8.is_contiguous() or out_u8.numel() != 3 * out_size * out_size):
+        raise ValueError("out_u8 must be contiguous uint8 [S, S, 3]")
+    if out_f32 is not None and (lut is None or lut.dtype != torch.float32 or lut.numel() != 768 or not lut.is_contiguous()):
+        raise ValueError("lut must be contiguous float32 [3, 256]")
+    rc = _L().groma_preprocess_image(_p(img), H, W, img.stride(0), _p(lut), out_size, _p(tmp), _p(coef), _p(out_f32), _p(out_u8),
+                                     _stream())
+    _chk(rc, "groma_preprocess_image")

@@ -201,6 +201,19 @@ int32_t groma_argmax(const float* logits, int64_t* out, int32_t rows, int32_t V,
 int32_t groma_cast_f32_bf16(const float* a, void* b, int64_t n, void* stream);
 int32_t groma_cast_bf16_f32(const void* a, float* b, int64_t n, void* stream);
 
+/* ---- image preprocessing in front of the ViT ----------------------------------------------------------
+ * Replaces, per image, the reference's CPU pass  PIL `Image.resize((448, 448))` (BICUBIC, uint8; groma/eval/run_groma.py:78,
+ * groma/data/datasets/groma.py:94) + `BitImageProcessor.preprocess` with do_resize=False, do_center_crop=False (rescale 1/255,
+ * ImageNet mean/std, CHW float32; run_groma.py:79, run_ddetr.py:39-45).
+ * img: uint8 RGB, HWC, row_stride bytes between rows (device).  The resize reproduces Pillow's two-pass fixed-point resampler
+ * bit for bit.  lut: float32 [3][256] = normalised value of every byte per channel (host computes it once with the processor's
+ * mean/std).  tmp: uint8 [H][out_size][3] scratch.  coef: int32 scratch of GROMA_PREPROCESS_COEF_INTS(out_size).
+ * out_f32: float32 [3][out_size][out_size] pixel_values (may be null), out_u8: resized uint8 [out_size][out_size][3] (may be null).
+ * Sides up to 15 x out_size. */
+#define GROMA_PREPROCESS_COEF_INTS(out_size) (2 * (out_size) * (2 + 64))
+int32_t groma_preprocess_image(const uint8_t* img, int32_t H, int32_t W, int64_t row_stride, const float* lut,
+                               int32_t out_size, uint8_t* tmp, int32_t* coef, float* out_f32, uint8_t* out_u8, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,14 +73,32 @@ class DetectionOutput:
 
 
 class CustomDDETRModel(torch.nn.Module):
-    """Detector-only entry (ddetr.py:169-196).  Shares the engine of a GromaModel when built through one; standalone
-    construction needs a full Groma state dict because the engine packs every stage at once."""
+    """Detector-only entry (ddetr.py:169-196).  Shares the engine of a GromaModel when built through one
+    (`GromaModel.perceiver`); `from_pretrained` on a detector checkpoint builds a detector-only engine."""
     config_class = CustomDDETRConfig
 
     def __init__(self, config: CustomDDETRConfig, engine=None):
         super().__init__()
         self.config = config
         self.engine = engine
+
+    @classmethod
+    def from_pretrained(cls, path: str, **kwargs) -> "CustomDDETRModel":
+        """Detector-only checkpoint written by the reference's `train_det.py` (keys `vis_encoder.*`, `input_proj.*`,
+        `ddetr_transformer.*`; reference ddetr.py:98-155), as `eval/run_ddetr.py:41` loads it."""
+        from groma_b200.checkpoint import ShardedStateDict, load_config_dict
+        from groma_b200.config import PathConfig
+        from groma_b200.engine import GromaEngine
+        cd = load_config_dict(path)
+        cd.pop("model_type", None)
+        config = CustomDDETRConfig(**cd)
+        return cls(config, engine=GromaEngine(PathConfig(**perceiver_fields(config)), ShardedStateDict(path), detector_only=True))
+
+    def cuda(self, device=None):
+        return self
+
+    def eval(self):
+        return self
 
     @torch.no_grad()
     def forward(self, images=None, labels=None, output_attentions=None, output_hidden_states=None, return_dict=None):

@@ -177,22 +177,20 @@ class GromaModel(torch.nn.Module):
     def from_pretrained(cls, path: str, torch_dtype=None, **kwargs) -> "GromaModel":
         if kwargs.get("load_in_8bit") or kwargs.get("quantization_config") is not None:
             raise NotImplementedError("8/4-bit loading would change results; the B200 path is bf16")
-        with open(os.path.join(path, "config.json")) as f:
-            cd = json.load(f)
+        from groma_b200.checkpoint import ShardedStateDict, load_config_dict
+        cd = load_config_dict(path)
         cd.pop("model_type", None)
         config = GromaConfig(**cd)
-        sd: Dict[str, torch.Tensor] = {}
-        st = sorted(glob.glob(os.path.join(path, "*.safetensors")))
-        if st:
-            from safetensors.torch import load_file
-            for fpath in st:
-                sd.update(load_file(fpath))
-        else:
-            for fpath in sorted(glob.glob(os.path.join(path, "pytorch_model*.bin"))):
-                sd.update(torch.load(fpath, map_location="cpu", weights_only=True))
-        if not sd:
-            raise FileNotFoundError(f"no *.safetensors / pytorch_model*.bin under {path}")
-        return cls(config, state_dict=sd)
+        # lazy view over the (sharded) checkpoint: the engine packs tensor by tensor into its bf16 device arena
+        view = ShardedStateDict(path)
+        # region-encoder widths are code constants in the reference (roi_align.py:97-116,233-271), not config fields:
+        # read them off the parameter shapes so any checkpoint of that architecture loads
+        re_ = "region_encoder."
+        geom = dict(region_mid=view.shape(re_ + "roi_align.flatten_linear.weight")[0],
+                    pos_hidden=view.shape(re_ + "roi_align.pos_embedd.0.weight")[0],
+                    fuse_rounds=sum(1 for k in view if k.startswith(re_ + "mlvl_fuse.fuse_convs.") and k.endswith(".conv.weight")))
+        geom.update(cd.get("path_overrides") or {})     # e.g. {"gn_groups": 8} for miniature test checkpoints (reference: 64)
+        return cls(config, state_dict=view, path_config=config.to_path_config(**geom))
 
     def cuda(self, device=None):
         return self

@@ -24,11 +24,16 @@ def _cat(*ts):
 
 
 class GromaEngine:
-    def __init__(self, cfg: PathConfig, state_dict: Dict[str, torch.Tensor], device: str = "cuda"):
+    def __init__(self, cfg: PathConfig, state_dict: Dict[str, torch.Tensor], device: str = "cuda", detector_only: bool = False):
+        """state_dict: any mapping key -> tensor with the reference's parameter names (a lazy `ShardedStateDict` reads each
+        tensor from its shard exactly when it is packed).  detector_only: a `CustomDDETRModel` checkpoint (keys without the
+        `perceiver.` prefix, no bridge / region encoder / LLaMA weights; reference ddetr.py:98-155) -- only vit() and
+        proposer() are usable."""
         if not torch.cuda.is_available():
             raise RuntimeError("GromaEngine needs a CUDA device: the B200 path has no CPU fallback")
         self.cfg = cfg
         self.dev = torch.device(device)
+        self.detector_only = detector_only
         self.w: Dict[str, torch.Tensor] = {}
         self._pack(state_dict)
         self._constants()
@@ -57,7 +62,8 @@ class GromaEngine:
     def _pack(self, sd: Dict[str, torch.Tensor]):
         cfg, w = self.cfg, self.w
         H, D, T = cfg.vit_hidden, cfg.d_model, cfg.llm_hidden
-        ve = "perceiver.vis_encoder."
+        pfx = "" if self.detector_only else "perceiver."
+        ve = pfx + "vis_encoder."
         pw = sd[ve + "embeddings.patch_embeddings.projection.weight"].reshape(H, -1).float()
         self.patch_ld = ((pw.shape[1] + 7) // 8) * 8
         pwp = torch.zeros(H, self.patch_ld)
@@ -75,12 +81,13 @@ class GromaEngine:
             w[o + "ln2.w"], w[o + "ln2.b"] = self._vec(sd[p + "norm2.weight"]), self._vec(sd[p + "norm2.bias"])
             w[o + "fc1.w"], w[o + "fc1.b"] = self._mat(sd[p + "mlp.fc1.weight"]), self._vec(sd[p + "mlp.fc1.bias"])
             w[o + "fc2.w"], w[o + "fc2.b"] = self._mat(sd[p + "mlp.fc2.weight"]), self._vec(sd[p + "mlp.fc2.bias"])
-        w["bridge0.w"], w["bridge0.b"] = self._mat(sd["img_txt_bridge.0.weight"]), self._vec(sd["img_txt_bridge.0.bias"])
-        w["bridge2.w"], w["bridge2.b"] = self._mat(sd["img_txt_bridge.2.weight"]), self._vec(sd["img_txt_bridge.2.bias"])
-        w["inproj.w"] = self._mat(sd["perceiver.input_proj.0.0.weight"].reshape(D, -1))
-        w["inproj.b"] = self._vec(sd["perceiver.input_proj.0.0.bias"])
-        w["inproj.ln.w"], w["inproj.ln.b"] = self._vec(sd["perceiver.input_proj.0.1.weight"]), self._vec(sd["perceiver.input_proj.0.1.bias"])
-        dt = "perceiver.ddetr_transformer."
+        if not self.detector_only:
+            w["bridge0.w"], w["bridge0.b"] = self._mat(sd["img_txt_bridge.0.weight"]), self._vec(sd["img_txt_bridge.0.bias"])
+            w["bridge2.w"], w["bridge2.b"] = self._mat(sd["img_txt_bridge.2.weight"]), self._vec(sd["img_txt_bridge.2.bias"])
+        w["inproj.w"] = self._mat(sd[pfx + "input_proj.0.0.weight"].reshape(D, -1))
+        w["inproj.b"] = self._vec(sd[pfx + "input_proj.0.0.bias"])
+        w["inproj.ln.w"], w["inproj.ln.b"] = self._vec(sd[pfx + "input_proj.0.1.weight"]), self._vec(sd[pfx + "input_proj.0.1.bias"])
+        dt = pfx + "ddetr_transformer."
 
         def lin(dst, src):
             w[dst + ".w"] = self._mat(sd[src + ".weight"])
@@ -119,6 +126,8 @@ class GromaEngine:
                 continue
             for j in range(3):
                 lin(f"bbox.{i}.{j}", f"{dt}bbox_embed.{i}.layers.{j}")
+        if self.detector_only:
+            return
         # region encoder
         re_ = "region_encoder."
         self.in_ld = H + 64

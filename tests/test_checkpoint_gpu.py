@@ -45,7 +45,8 @@ def test_groma_from_pretrained_matches_in_memory(tmp_path, fmt, max_bytes):
         o = m.generate(ids.clone().cuda(), images=images.cuda(), max_new_tokens=6, return_dict_in_generate=True, output_hidden_states=True)
         outs.append(o)
     assert torch.equal(outs[0].sequences, outs[1].sequences)
-    assert torch.equal(outs[0].hidden_states[0][-1]["pred_boxes"], outs[1].hidden_states[0][-1]["pred_boxes"])
+    pa, pb = outs[0].hidden_states[0][-1]["pred_boxes"], outs[1].hidden_states[0][-1]["pred_boxes"]   # per-image box lists
+    assert len(pa) == len(pb) and all(torch.equal(x, y) for x, y in zip(pa, pb))
 
 
 def test_detector_checkpoint_from_pretrained(tmp_path):

@@ -345,11 +345,13 @@ def decode_gemm_roofline(model, B, args, step):
     ach = nbytes / (ms / 1000.0) / 1e9
     return {"kernel": "gemm_bf16_tcgen05_kernel<16> (swap-AB weight-streaming GEMM of the decode step; 129 launches per step)",
             "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": 187684096, "traffic_note": "dram read+write of the gate/up launch from ncu --set full (profiles/r01_decode_gemm_swapab_gateup.md): "
-                                                  "180.55 MB + 7.13 MB for 180.4 MB of weights; null for the other four shapes",
+            "traffic": 188094464, "traffic_note": "dram read+write of the gate/up launch (split_k 5) from ncu --set full "
+                                                  "(profiles/r01_decode_gemm_swapab_gateup_v2.md): 180.60 MB + 7.50 MB for 180.4 MB of weights + "
+                                                  "7.0 MB of fp32 partials; not captured for the other four shapes",
             "peak_source": how, "launches_timed": len(names) * reps, "avg_launch_us": ms * 1000.0 / len(names),
             "algorithmic_bytes_per_launch": nbytes / len(names),
-            "read_only_ceiling_note": "torch.sum over 1 GiB reaches 5.52 TB/s on this box; the 6.58 TB/s peak is a copy (read+write)"}
+            "read_only_ceiling_note": "the 6.58 TB/s peak is a copy (read+write); a read-only stream reaches 7.35 TB/s on this part "
+                                      "(tools/cu/read_bw.cu, LDG.128 or 1-D bulk TMA), so frac vs read-only would be achieved/7350"}
 
 
 if __name__ == "__main__":

@@ -52,7 +52,7 @@ class GromaImageProcessor:
             t = img
         else:
             if hasattr(img, "convert"):           # PIL.Image: same `.convert('RGB')` the reference applies
-                img = np.asarray(img.convert("RGB"))
+                img = np.array(img.convert("RGB"))            # writable copy
             t = torch.from_numpy(np.ascontiguousarray(img))
         if t.dtype != torch.uint8 or t.dim() != 3 or t.shape[2] != 3:
             raise ValueError(f"expected an RGB uint8 HWC image, got {tuple(t.shape)} {t.dtype}")

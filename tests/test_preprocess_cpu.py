@@ -47,3 +47,18 @@ def test_full_pipeline_against_reference_call_sequence():
     pil = PIL.fromarray(img, "RGB").resize((448, 448))                      # run_groma.py:78
     want = proc.preprocess(pil, return_tensors="np")["pixel_values"][0]   # run_groma.py:79
     np.testing.assert_allclose(P.preprocess_ref(img), want, rtol=0, atol=2.5e-7)
+
+
+def test_processor_host_logic_without_gpu():
+    """Host side of GromaImageProcessor: the byte table equals the oracle's, inputs are validated, PIL images are converted."""
+    import torch
+    from groma_b200.preprocess import GromaImageProcessor, _byte_table, IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD
+    assert np.array_equal(_byte_table(IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD, 1 / 255), P.normalize_lut())
+    t = GromaImageProcessor._to_hwc_u8(PIL.fromarray(np.zeros((5, 7, 3), dtype=np.uint8), "RGB"))
+    assert t.dtype == torch.uint8 and tuple(t.shape) == (5, 7, 3)
+    t = GromaImageProcessor._to_hwc_u8(PIL.fromarray(np.zeros((5, 7), dtype=np.uint8), "L"))      # .convert('RGB') as the reference does
+    assert tuple(t.shape) == (5, 7, 3)
+    with pytest.raises(ValueError):
+        GromaImageProcessor._to_hwc_u8(np.zeros((5, 7, 3), dtype=np.float32))
+    with pytest.raises(ValueError):
+        GromaImageProcessor().preprocess([np.zeros((5, 7, 3), dtype=np.uint8)], return_tensors="np")

@@ -3,6 +3,7 @@
 // Serves: LLaMA prefill + decode (modeling_llama.py:199-289 semantics), DINOv2 global attention
 // (modeling_dinov2.py:153-179) and the DDETR decoder self-attention (modeling_deformable_detr.py:453-516).
 #include "ptx.cuh"
+#include "decode_common.cuh"
 #include "capi_common.h"
 #include <cooperative_groups.h>
 #include <cstdlib>
@@ -423,11 +424,24 @@ constexpr int DT_KEYS = DEC_WARPS * 2 * DT_UNROLL;   // keys per stage (16)
 #endif
 constexpr int DT_STAGES = GROMA_DT_STAGES;
 
-template <int D>
+// ROPE = true additionally folds the kernel in front of it into the prologue (one launch less per layer): q, and the new
+// token's K/V row, are reduced from the qkv GEMM's split-K partials ws[S][B][3*H*D] and rotated exactly as
+// reduce_rope_kv_kernel does (shared code in decode_common.cuh); the CTA whose key range holds position *pos_ptr writes the
+// new K/V row into the cache and substitutes it for the (stale) staged copy when that key comes up, so the key order -- and
+// every bit of the result -- is that of reduce_rope_kv_kernel followed by the ROPE = false kernel.
+struct DecodeRopeArgs {
+    const float* ws; int S;
+    const float* cos_t; const float* sin_t;
+    const int* pos_ptr;
+};
+
+template <int D, bool ROPE>
 __global__ void __cluster_dims__(DEC_SPLIT, 1, 1) __launch_bounds__((DEC_WARPS + 1) * 32) decode_attention_tma_kernel(
-    const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc, const __nv_bfloat16* __restrict__ vc,
-    __nv_bfloat16* __restrict__ out, const int* __restrict__ kv_len, int H, long long cap, float scale_log2) {
+    const __nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ kc, __nv_bfloat16* __restrict__ vc,
+    __nv_bfloat16* __restrict__ out, const int* __restrict__ kv_len, int H, long long cap, float scale_log2, DecodeRopeArgs ra) {
     static_assert(D == 128, "16 lanes x 8 dims");
+    static_assert(!ROPE || DEC_WARPS * 32 == D / 2, "one consumer thread per rotary pair");
+    __shared__ __align__(16) __nv_bfloat16 s_new[3][D];   // ROPE: q, new k row, new v row
     __shared__ __align__(128) __nv_bfloat16 ring[DT_STAGES][2][DT_KEYS * D];
     __shared__ __align__(8) uint64_t full_bar[DT_STAGES], empty_bar[DT_STAGES];
     __shared__ float sm_m[DEC_WARPS * 2], sm_l[DEC_WARPS * 2], sm_acc[DEC_WARPS * 2][D];
@@ -450,8 +464,15 @@ __global__ void __cluster_dims__(DEC_SPLIT, 1, 1) __launch_bounds__((DEC_WARPS +
     const int k_begin = min(crank * per, n_all);
     const int n = min(n_all, k_begin + per) - k_begin;
     const int nchunks = (n + DT_KEYS - 1) / DT_KEYS;
-    const __nv_bfloat16* kb = kc + (((long long)b * H + h) * cap + k_begin) * D;
-    const __nv_bfloat16* vb = vc + (((long long)b * H + h) * cap + k_begin) * D;
+    __nv_bfloat16* kb = kc + (((long long)b * H + h) * cap + k_begin) * D;
+    __nv_bfloat16* vb = vc + (((long long)b * H + h) * cap + k_begin) * D;
+    int newidx = -1;          // ROPE: index (within this CTA's key range) of the token appended by this step, if it is ours
+    bool append = false;      // ROPE: this CTA writes the new K/V row (the range owner; the last CTA if no range holds it)
+    if constexpr (ROPE) {
+        const int pos = *ra.pos_ptr;
+        if (pos >= k_begin && pos < k_begin + n) newidx = pos - k_begin;
+        append = newidx >= 0 || (pos >= n_all && crank == DEC_SPLIT - 1);
+    }
     if (warp == DEC_WARPS) {
         if (lane == 0) {
             int stage = 0;
@@ -468,8 +489,34 @@ __global__ void __cluster_dims__(DEC_SPLIT, 1, 1) __launch_bounds__((DEC_WARPS +
         }
     } else {
         float qf[8];
+        if constexpr (ROPE) {
+            constexpr int half = D / 2;
+            const int j = threadIdx.x;                       // one rotary pair (j, j + half) per consumer thread
+            const int N = 3 * H * D;
+            const int pos = *ra.pos_ptr;
+            const float c = ra.cos_t[(long long)pos * half + j], sn = ra.sin_t[(long long)pos * half + j];
+            float q1, q2;
+            splitk_pair(ra.ws, ra.S, (int)gridDim.y, N, b, h * D, j, half, q1, q2);
+            q1 = bf16_round(q1); q2 = bf16_round(q2);
+            rope_pair(q1, q2, c, sn, s_new[0][j], s_new[0][j + half]);
+            if (append) {
+                float k1, k2, v1, v2;
+                splitk_pair(ra.ws, ra.S, (int)gridDim.y, N, b, H * D + h * D, j, half, k1, k2);
+                splitk_pair(ra.ws, ra.S, (int)gridDim.y, N, b, 2 * H * D + h * D, j, half, v1, v2);
+                k1 = bf16_round(k1); k2 = bf16_round(k2);
+                rope_pair(k1, k2, c, sn, s_new[1][j], s_new[1][j + half]);
+                s_new[2][j] = __float2bfloat16_rn(v1);
+                s_new[2][j + half] = __float2bfloat16_rn(v2);
+                __nv_bfloat16* kn = kc + (((long long)b * H + h) * cap + pos) * D;   // append to the cache for the following steps
+                __nv_bfloat16* vn = vc + (((long long)b * H + h) * cap + pos) * D;
+                kn[j] = s_new[1][j]; kn[j + half] = s_new[1][j + half];
+                vn[j] = s_new[2][j]; vn[j + half] = s_new[2][j + half];
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(DEC_WARPS * 32) : "memory");   // consumer warps only
+        }
         {
-            const uint4 qv = *reinterpret_cast<const uint4*>(q + ((long long)b * H + h) * D + l * 8);
+            const uint4 qv = ROPE ? *reinterpret_cast<const uint4*>(&s_new[0][l * 8])
+                                  : *reinterpret_cast<const uint4*>(q + ((long long)b * H + h) * D + l * 8);
             const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&qv);
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
@@ -494,8 +541,12 @@ __global__ void __cluster_dims__(DEC_SPLIT, 1, 1) __launch_bounds__((DEC_WARPS +
             for (int u = 0; u < DT_UNROLL; ++u) {
                 const int j = slot + u * STEP;
                 const bool ok = j < left;
-                const uint4 kk = ok ? *reinterpret_cast<const uint4*>(ks + j * D + l * 8) : make_uint4(0, 0, 0, 0);
+                uint4 kk = ok ? *reinterpret_cast<const uint4*>(ks + j * D + l * 8) : make_uint4(0, 0, 0, 0);
                 vv[u] = ok ? *reinterpret_cast<const uint4*>(vs + j * D + l * 8) : make_uint4(0, 0, 0, 0);
+                if (ROPE && c * DT_KEYS + j == newidx) {     // this step's token: its staged copy predates the append
+                    kk = *reinterpret_cast<const uint4*>(&s_new[1][l * 8]);
+                    vv[u] = *reinterpret_cast<const uint4*>(&s_new[2][l * 8]);
+                }
                 const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kk);
                 float d = 0.f;
 #pragma unroll
@@ -601,12 +652,33 @@ GROMA_API int32_t groma_decode_attention(const void* q, const void* cache_k, con
     if (use_tma < 0) { const char* ev = getenv("GROMA_DEC_ATTN_TMA"); use_tma = ev ? atoi(ev) : 1; }
     if (use_tma) {
         cfg.blockDim = dim3((gb::DEC_WARPS + 1) * 32);
-        e = cudaLaunchKernelEx(&cfg, gb::decode_attention_tma_kernel<128>, Q, K, V, O, kv_len, (int)H, (long long)cap, sl2);
+        e = cudaLaunchKernelEx(&cfg, gb::decode_attention_tma_kernel<128, false>, Q, const_cast<__nv_bfloat16*>(K),
+                               const_cast<__nv_bfloat16*>(V), O, kv_len, (int)H, (long long)cap, sl2, gb::DecodeRopeArgs{});
         return e == cudaSuccess ? GROMA_OK : GROMA_ERR_CUDA;
     }
     if (unroll == 8) e = cudaLaunchKernelEx(&cfg, gb::decode_attention_kernel<128, 8>, Q, K, V, O, kv_len, (int)H, (long long)cap, sl2);
     else if (unroll == 6) e = cudaLaunchKernelEx(&cfg, gb::decode_attention_kernel<128, 6>, Q, K, V, O, kv_len, (int)H, (long long)cap, sl2);
     else if (unroll == 2) e = cudaLaunchKernelEx(&cfg, gb::decode_attention_kernel<128, 2>, Q, K, V, O, kv_len, (int)H, (long long)cap, sl2);
     else e = cudaLaunchKernelEx(&cfg, gb::decode_attention_kernel<128, 4>, Q, K, V, O, kv_len, (int)H, (long long)cap, sl2);
+    return e == cudaSuccess ? GROMA_OK : GROMA_ERR_CUDA;
+}
+
+GROMA_API int32_t groma_decode_rope_attention(const float* ws, int32_t splits, void* cache_k, void* cache_v, void* out,
+                                              const int32_t* kv_len, const int32_t* pos_ptr, const float* cos_t, const float* sin_t,
+                                              int32_t B, int32_t H, int32_t D, int64_t cap, float scale, int32_t pdl, void* stream) {
+    if (!ws || !cache_k || !cache_v || !out || !kv_len || !pos_ptr || !cos_t || !sin_t || B <= 0 || H <= 0 || splits < 1) return GROMA_ERR_ARG;
+    if (D != 128) return GROMA_ERR_UNSUPPORTED;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(H * gb::DEC_SPLIT, B); cfg.blockDim = dim3((gb::DEC_WARPS + 1) * 32); cfg.dynamicSmemBytes = 0;
+    cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    if (pdl) { cfg.attrs = attr; cfg.numAttrs = 1; }
+    gb::DecodeRopeArgs ra{ws, splits, cos_t, sin_t, pos_ptr};
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gb::decode_attention_tma_kernel<128, true>, (const __nv_bfloat16*)nullptr,
+                                       reinterpret_cast<__nv_bfloat16*>(cache_k), reinterpret_cast<__nv_bfloat16*>(cache_v),
+                                       reinterpret_cast<__nv_bfloat16*>(out), kv_len, (int)H, (long long)cap,
+                                       scale * 1.4426950408889634f, ra);
     return e == cudaSuccess ? GROMA_OK : GROMA_ERR_CUDA;
 }

@@ -8,6 +8,7 @@
 // All kernels are programmatic-dependent-launch aware: they trigger their dependents at entry and wait for their
 // producer before touching memory, so launch latency overlaps the previous kernel (they are a few microseconds long).
 #include "ptx.cuh"
+#include "decode_common.cuh"
 #include "capi_common.h"
 #include <cooperative_groups.h>
 
@@ -157,22 +158,17 @@ __global__ void reduce_rope_kv_kernel(const float* __restrict__ ws, int S, int B
         long long r = i / half;
         const int h = r % H;
         const int b = r / H;
-        float q1 = 0.f, q2 = 0.f, k1 = 0.f, k2 = 0.f, v1 = 0.f, v2 = 0.f;
-        for (int s = 0; s < S; ++s) {
-            const float* row = ws + ((long long)s * B + b) * N + h * D + j;
-            q1 += __ldcg(row); q2 += __ldcg(row + half);
-            k1 += __ldcg(row + H * D); k2 += __ldcg(row + H * D + half);
-            v1 += __ldcg(row + 2 * H * D); v2 += __ldcg(row + 2 * H * D + half);
-        }
+        float q1, q2, k1, k2, v1, v2;
+        splitk_pair(ws, S, B, N, b, h * D, j, half, q1, q2);
+        splitk_pair(ws, S, B, N, b, H * D + h * D, j, half, k1, k2);
+        splitk_pair(ws, S, B, N, b, 2 * H * D + h * D, j, half, v1, v2);
         // the un-fused path stores qkv in bf16 before RoPE: keep that rounding point
         q1 = bf16_round(q1); q2 = bf16_round(q2); k1 = bf16_round(k1); k2 = bf16_round(k2);
         const float c = cos_t[(long long)pos * half + j], sn = sin_t[(long long)pos * half + j];
         __nv_bfloat16* qo = q_out + (long long)b * H * D + h * D;
-        qo[j] = __float2bfloat16_rn(q1 * c - q2 * sn);
-        qo[j + half] = __float2bfloat16_rn(q2 * c + q1 * sn);
+        rope_pair(q1, q2, c, sn, qo[j], qo[j + half]);
         const long long co = (((long long)b * H + h) * cap + pos) * D;
-        cache_k[co + j] = __float2bfloat16_rn(k1 * c - k2 * sn);
-        cache_k[co + j + half] = __float2bfloat16_rn(k2 * c + k1 * sn);
+        rope_pair(k1, k2, c, sn, cache_k[co + j], cache_k[co + j + half]);
         cache_v[co + j] = __float2bfloat16_rn(v1);
         cache_v[co + j + half] = __float2bfloat16_rn(v2);
     }

@@ -49,6 +49,7 @@ class GromaEngine:
         # stays opt-in until the two-Q-tile ping-pong version lands
         self.use_tc_attention = False
         self.fused_decode = True     # fused reduce epilogues + PDL in the decode step
+        self.fused_rope_attn = os.environ.get("GROMA_FUSED_ROPE_ATTN", "1") == "1"   # qkv reduce + RoPE + KV append inside the attention launch
         self.use_pdl = True
         self.timing_hook = None   # bench.py: list collecting (start_event, end_event, algorithmic_bytes) per swap-AB GEMM
 
@@ -585,12 +586,15 @@ class GromaEngine:
             o = f"llm.{i}."
             kc, vc = self.kv[i, 0], self.kv[i, 1]
             ws = gemm(y, o + "qkv.w", sp["qkv"])
-            G.decode_reduce_rope_kv(ws, d["q"], kc, vc, self.rope_cos, self.rope_sin, d["pos"], nh, hd, pdl=pdl)
-            if hd == 128:
-                G.decode_attention(d["q"], kc, vc, d["kv_len"], 1.0 / math.sqrt(hd), d["a"], pdl=pdl)
+            if hd == 128 and self.fused_rope_attn:
+                G.decode_rope_attention(ws, kc, vc, d["kv_len"], d["pos"], self.rope_cos, self.rope_sin, 1.0 / math.sqrt(hd), d["a"], pdl=pdl)
             else:
-                G.attention(d["q"].reshape(B, 1, nh, hd), kc, vc, causal=False, scale=1.0 / math.sqrt(hd), kv_len=d["kv_len"],
-                            out=d["a"], sk=self.kv_cap)
+                G.decode_reduce_rope_kv(ws, d["q"], kc, vc, self.rope_cos, self.rope_sin, d["pos"], nh, hd, pdl=pdl)
+                if hd == 128:
+                    G.decode_attention(d["q"], kc, vc, d["kv_len"], 1.0 / math.sqrt(hd), d["a"], pdl=pdl)
+                else:
+                    G.attention(d["q"].reshape(B, 1, nh, hd), kc, vc, causal=False, scale=1.0 / math.sqrt(hd), kv_len=d["kv_len"],
+                                out=d["a"], sk=self.kv_cap)
             ws = gemm(d["a"].reshape(B, Hd), o + "o.w", sp["o"])
             G.decode_reduce_norm(ws, x, w[o + "ln2"], y, cfg.rms_eps, pdl=pdl)
             ws = gemm(y, o + "gu.w", sp["gu"])

@@ -527,6 +527,18 @@ def decode_reduce_rope_kv(ws: torch.Tensor, q_out: torch.Tensor, cache_k: torch.
                                           _p(pos_ptr), cache_k.shape[2], 1 if pdl else 0, _stream()), "groma_decode_reduce_rope_kv")
 
 
+def decode_rope_attention(ws: torch.Tensor, cache_k: torch.Tensor, cache_v: torch.Tensor, kv_len: torch.Tensor, pos_ptr: torch.Tensor,
+                          cos_t: torch.Tensor, sin_t: torch.Tensor, scale: float, out: torch.Tensor, pdl: bool = True) -> torch.Tensor:
+    """decode_reduce_rope_kv + decode_attention in one launch: ws [S, B, 3*H*D] fp32 qkv partials; the new K/V row is appended
+    to cache_k/v [B, H, cap, 128] at *pos_ptr; out [B, H*D] bf16."""
+    S, B, N = ws.shape
+    _, H, cap, D = cache_k.shape
+    assert N == 3 * H * D and cache_k.is_contiguous() and cache_v.is_contiguous() and out.is_contiguous() and ws.is_contiguous()
+    _chk(_L().groma_decode_rope_attention(_p(ws), S, _p(cache_k), _p(cache_v), _p(out), _p(kv_len), _p(pos_ptr), _p(cos_t), _p(sin_t),
+                                          B, H, D, cap, float(scale), 1 if pdl else 0, _stream()), "groma_decode_rope_attention")
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # image preprocessing (SURVEY §8f N3)
 PREPROCESS_KMAX = 64

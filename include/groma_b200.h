@@ -91,6 +91,14 @@ int32_t groma_attention_tc(const void* q, int64_t q_rows, int64_t q_cols, int64_
 int32_t groma_decode_attention(const void* q, const void* cache_k, const void* cache_v, void* out, const int32_t* kv_len,
                                int32_t B, int32_t H, int32_t D, int64_t cap, float scale, int32_t pdl, void* stream);
 
+/* groma_decode_reduce_rope_kv + groma_decode_attention in one launch (decode step, D = 128): q and the new token's K/V row
+ * are reduced from the qkv GEMM's split-K partials ws[splits][B][3*H*D], rotated (rotate-half RoPE at position *pos_ptr,
+ * $HF/models/llama/modeling_llama.py:138-168), the K/V row is appended to the cache at *pos_ptr (the tuple-cache torch.cat of
+ * groma.py:376-379) and the attention over kv_len[b] positions follows; bit-identical to the two separate calls. */
+int32_t groma_decode_rope_attention(const float* ws, int32_t splits, void* cache_k, void* cache_v, void* out,
+                                    const int32_t* kv_len, const int32_t* pos_ptr, const float* cos_t, const float* sin_t,
+                                    int32_t B, int32_t H, int32_t D, int64_t cap, float scale, int32_t pdl, void* stream);
+
 /* y = w * bf16(h * rsqrt(mean(h^2)+eps)), h = bf16(x + residual) (h_out optional).  LlamaRMSNorm,
  * $HF/models/llama/modeling_llama.py:53-70 (+ the residual add of :292-340). */
 int32_t groma_rmsnorm(const void* x, const void* residual, const float* w, void* y, void* h_out, int64_t rows,

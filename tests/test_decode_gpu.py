@@ -133,3 +133,35 @@ def test_fused_decode_step_is_bit_identical_to_unfused():
         assert torch.equal(lg, base_lg), k    # tiny model: N=256 < 1024 keeps the single-CTA reduce -> bit-identical
     # all fused variants agree with each other bit for bit (same kernels; PDL / graph only change scheduling)
     assert torch.equal(runs[(True, False, False)][1], runs[(True, True, True)][1])
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_rope_attention_fusion_is_bit_identical(G, ragged):
+    """groma_decode_rope_attention == groma_decode_reduce_rope_kv followed by groma_decode_attention: attention output and the
+    appended K/V rows, bit for bit (head_dim 128, the Groma-7B shape; the miniature model's decode uses head_dim 32)."""
+    torch.manual_seed(5)
+    B, H, D, cap, S, pos = 5, 4, 128, 300, 3, 257
+    dev = "cuda"
+    ws = torch.randn(S, B, 3 * H * D, device=dev)
+    kc0 = torch.randn(B, H, cap, D, device=dev).bfloat16()
+    vc0 = torch.randn(B, H, cap, D, device=dev).bfloat16()
+    ang = torch.rand(cap, D // 2, device=dev) * 6.28
+    cos_t, sin_t = ang.cos().contiguous(), ang.sin().contiguous()
+    pos_t = torch.tensor([pos], dtype=torch.int32, device=dev)
+    kv = [pos + 1] * B
+    if ragged:
+        kv = [pos + 1, 17, pos, 1, 130]          # rows whose visible range does not include the appended position
+    kv_len = torch.tensor(kv, dtype=torch.int32, device=dev)
+    scale = 1.0 / math.sqrt(D)
+    k1, v1 = kc0.clone(), vc0.clone()
+    q = torch.empty(B, H * D, device=dev, dtype=torch.bfloat16)
+    a1 = torch.empty(B, H * D, device=dev, dtype=torch.bfloat16)
+    G.decode_reduce_rope_kv(ws, q, k1, v1, cos_t, sin_t, pos_t, H, D, pdl=False)
+    G.decode_attention(q, k1, v1, kv_len, scale, a1)
+    k2, v2 = kc0.clone(), vc0.clone()
+    a2 = torch.empty_like(a1)
+    G.decode_rope_attention(ws, k2, v2, kv_len, pos_t, cos_t, sin_t, scale, a2, pdl=False)
+    torch.cuda.synchronize()
+    assert torch.equal(k1, k2) and torch.equal(v1, v2)
+    assert not torch.equal(k1[:, :, pos], kc0[:, :, pos])          # the row really was appended
+    assert torch.equal(a1, a2)

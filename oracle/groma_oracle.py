@@ -5,9 +5,12 @@ Pure PyTorch on CPU tensors; no mmcv / mmdet / HF-model imports.  Each function 
 5.5 sources where the arithmetic is unchanged -- see SURVEY.md section 8c).
 
 PARITY STATUS: the native ops used here (oracle/ops.py: nms, roi_align, msda) are pinned against the reference's golden
-vectors and its own compiled C++ CPU kernels (tests/test_oracle_pinned.py).  Model level (GromaModel.forward, DDETR
-glue, region encoder, Dinov2, Llama): **parity unpinned** -- the reference holds no test, fixture or recorded output
-for it and cannot be imported in this image; this restatement + tests/golden/ become the pin.
+vectors and its own compiled C++ CPU kernels (tests/test_oracle_pinned.py).  The third-party sub-models restated here
+(Dinov2 stack, LLaMA prefill + cached decode, Deformable-DETR sine embedding / encoder layers / decoder layers) are pinned
+against the transformers modules installed in this image on identical weights (tests/test_oracle_hf_pins_cpu.py).
+The reference's own glue (GromaModel.forward, DeformableDetrDecoderX wiring, two-stage head, region selection, region
+encoder): **parity unpinned** -- the reference holds no test, fixture or recorded output for it and cannot be imported in
+this image; this restatement + tests/golden/ become the pin.
 
 Precision modes (`prec`):
   'fp32' : plain fp32 everywhere = the reference's fp32 inference arithmetic (eval_rec.py:69).
@@ -256,7 +259,8 @@ class Oracle:
         coco = self.lin(keep[L - 1], f"{dt}class_embed_coco.{L - 1}", out_round=False)[..., 0]
         sa1b = self.lin(keep[L - 1], f"{dt}class_embed_sa1b.{L - 1}", out_round=False)[..., 0]
         scores = coco.sigmoid() ** 0.4 * sa1b.sigmoid() ** 0.6                    # groma.py:247-249
-        self.stages.update(dict(ddetr_src=src, memory=memory, enc_cls=cls, topk=topk, ref_init=ref, dec_last=keep[L - 1]))
+        self.stages.update(dict(ddetr_src=src, memory=memory, enc_cls=cls, topk=topk, ref_init=ref, dec_last=keep[L - 1],
+                                query_pos=query_pos, tgt=r(self.W(dt + "query_position_embeddings.weight"))[None].expand(B, -1, -1)))
         return pred, scores, {"coco": coco, "sa1b": sa1b}
 
     # ------------------------------------------------------------------ a10: region selection (groma.py:251-280)

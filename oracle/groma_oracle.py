@@ -260,6 +260,7 @@ class Oracle:
         sa1b = self.lin(keep[L - 1], f"{dt}class_embed_sa1b.{L - 1}", out_round=False)[..., 0]
         scores = coco.sigmoid() ** 0.4 * sa1b.sigmoid() ** 0.6                    # groma.py:247-249
         self.stages.update(dict(ddetr_src=src, memory=memory, enc_cls=cls, topk=topk, ref_init=ref, dec_last=keep[L - 1],
+                                enc_obj_query=eo, prop_logit=prop_logit, topk_coord_logits=tk, pos512=pos512,
                                 query_pos=query_pos, tgt=r(self.W(dt + "query_position_embeddings.weight"))[None].expand(B, -1, -1)))
         return pred, scores, {"coco": coco, "sa1b": sa1b}
 

@@ -148,3 +148,31 @@ def test_ddetr_decoder_layers_match_hf(setup):
                       encoder_hidden_states=memory, encoder_attention_mask=None)
             h = h[0] if isinstance(h, tuple) else h
     close(want, h)
+
+
+def test_two_stage_proposal_helpers_match_hf(setup):
+    """gen_encoder_output_proposals / get_proposal_pos_embed (reference copies: ddetr_transformer.py:383-446) against the
+    transformers implementations, called on a stub that carries the same enc_output / enc_output_norm parameters."""
+    from types import SimpleNamespace
+    cfg, sd, o = setup
+    M, dc = _ddetr_modules(cfg)
+    g0 = torch.Generator().manual_seed(4)
+    o.proposer(o.vit(torch.randn(2, 3, 518, 518, generator=g0)))
+    st = o.stages
+    memory = st["memory"]
+    B, S, D = memory.shape
+    g = cfg.grid
+    dt = "perceiver.ddetr_transformer."
+    lin = torch.nn.Linear(D, D)
+    ln = torch.nn.LayerNorm(D, eps=1e-5)
+    lin.load_state_dict({"weight": sd[dt + "enc_output.weight"].float(), "bias": sd[dt + "enc_output.bias"].float()})
+    ln.load_state_dict({"weight": sd[dt + "enc_output_norm.weight"].float(), "bias": sd[dt + "enc_output_norm.bias"].float()})
+    stub = SimpleNamespace(enc_output=lin, enc_output_norm=ln, config=dc)
+    with torch.no_grad():
+        oq, props = M.DeformableDetrModel.gen_encoder_output_proposals(stub, memory, torch.zeros(B, S, dtype=torch.bool), torch.tensor([[g, g]]))
+        pos = M.DeformableDetrModel.get_proposal_pos_embed(stub, st["topk_coord_logits"])
+    close(st["enc_obj_query"], oq)
+    finite = torch.isfinite(props[0])
+    assert torch.equal(finite, torch.isfinite(st["prop_logit"]))                  # same (0.01, 0.99) validity mask
+    close(st["prop_logit"][finite], props[0][finite], tol=1e-6)
+    close(st["pos512"], pos, tol=1e-5)

@@ -8,9 +8,10 @@ PARITY STATUS: the native ops used here (oracle/ops.py: nms, roi_align, msda) ar
 vectors and its own compiled C++ CPU kernels (tests/test_oracle_pinned.py).  The third-party sub-models restated here
 (Dinov2 stack, LLaMA prefill + cached decode, Deformable-DETR sine embedding / encoder layers / decoder layers) are pinned
 against the transformers modules installed in this image on identical weights (tests/test_oracle_hf_pins_cpu.py).
-The reference's own glue (GromaModel.forward, DeformableDetrDecoderX wiring, two-stage head, region selection, region
-encoder): **parity unpinned** -- the reference holds no test, fixture or recorded output for it and cannot be imported in
-this image; this restatement + tests/golden/ become the pin.
+The reference's own glue (GromaModel.forward prefill + decode branch, DeformableDetrTransformer / DeformableDetrDecoderX, region
+selection, MLVLROIQueryModule) is pinned against outputs of the reference's own source files, executed in the authoring
+container under leaf adapters and committed as fixtures (tests/golden/make_*_golden.py, tests/test_*_ref_cpu.py); the reference
+holds no test or recorded output of its own for this level.
 
 Precision modes (`prec`):
   'fp32' : plain fp32 everywhere = the reference's fp32 inference arithmetic (eval_rec.py:69).
@@ -387,6 +388,19 @@ class Oracle:
                     labels[i].masked_scatter_(mask, ids)
         return refer_inds
 
+    def assemble_labels(self, input_ids: torch.Tensor, labels: torch.Tensor, num_regions: List[int], n_img_tokens: int):
+        """groma.py:338-353: labels follow the same expansion with IGNORE_INDEX (-100) under the image / region placeholders."""
+        t = self.tok
+        new = []
+        for i in range(input_ids.shape[0]):
+            ids, lab = input_ids[i], labels[i]
+            ip = int((ids == t["img"]).nonzero()[0]); rp = int((ids == t["reg"]).nonzero()[0])
+            pp = (ids == t["pad"]).nonzero()
+            pe = int(pp[0]) if len(pp) > 0 else len(ids)
+            new.append(torch.cat((lab[:ip], torch.full((n_img_tokens,), -100, dtype=torch.long), lab[ip + 1:rp],
+                                  torch.full((2 * num_regions[i],), -100, dtype=torch.long), lab[rp + 1:pe])))
+        return torch.nn.utils.rnn.pad_sequence(new, batch_first=True, padding_value=-100)
+
     def assemble(self, input_ids: torch.Tensor, num_regions: List[int], n_img_tokens: int):
         """groma.py:317-357: expand <image>/<region> placeholders, cut at first pad, right-pad."""
         t = self.tok
@@ -457,7 +471,7 @@ class Oracle:
         return h @ w.t()   # fp32
 
     # ------------------------------------------------------------------ GromaModel.forward, prefill branch (groma.py:217-402)
-    def forward_prefill(self, input_ids, images, refer_boxes=None, ground_boxes=None, selected_override=None):
+    def forward_prefill(self, input_ids, images, refer_boxes=None, ground_boxes=None, selected_override=None, labels=None):
         assert self.tok is not None
         hs = self.vit(images)
         self.stages["vit_last"] = hs[-1]
@@ -467,7 +481,7 @@ class Oracle:
             selected, nms_inds = selected_override, None
         else:
             selected, nms_inds = self.select_regions(pred, scores, refer_boxes, ground_boxes)
-        refer_inds = self.match_refer_ground(input_ids, selected, refer_boxes, ground_boxes)
+        refer_inds = self.match_refer_ground(input_ids, selected, refer_boxes, ground_boxes, labels)
         region = self.region_encoder(hs, selected)
         refer_feats = [rf[ind] for rf, ind in zip(region, refer_inds)]
         ids, mask = self.assemble(input_ids, [len(x) for x in region], img_tok.shape[1])
@@ -482,6 +496,11 @@ class Oracle:
         out = dict(logits=self.logits(h), kv=kv, input_ids=ids, attention_mask=mask, pred_boxes=pred, scores=scores,
                    det_logits=logits, selected_boxes=selected, nms_inds=nms_inds, image_features=img_tok,
                    region_features=torch.cat(region), inputs_embeds=x)
+        if labels is not None:      # groma.py:404-415: shifted cross entropy, mean over the non-ignored targets
+            lab = self.assemble_labels(input_ids, labels, [len(x) for x in region], img_tok.shape[1])
+            lg = out["logits"]
+            out["labels"] = lab
+            out["loss"] = F.cross_entropy(lg[:, :-1].reshape(-1, lg.shape[-1]).float(), lab[:, 1:].reshape(-1), ignore_index=-100)
         return out
 
     def forward_decode(self, token_ids, kv):

@@ -172,8 +172,10 @@ def run_reference(seed=1234):
                          use_cache=True, return_dict=True)
                 dec_logits.append(step.logits[:, 0].clone())
                 tok_ids = step.logits[:, 0].argmax(-1)
+            det = m.perceiver(images, return_dict=True)                # detector-only entry, ddetr.py:169-196 (eval/run_ddetr.py:49-50)
         vis_out = out.hidden_states[1]
-        return dict(logits=out.logits, loss=out.loss, input_ids_after=ids_in, selected_boxes=[b.clone() for b in vis_out["pred_boxes"]],
+        return dict(det_pred_boxes=det.pred_boxes, det_coco=det.logits["coco"], det_sa1b=det.logits["sa1b"],
+                    logits=out.logits, loss=out.loss, input_ids_after=ids_in, selected_boxes=[b.clone() for b in vis_out["pred_boxes"]],
                     image_features=vis_out["image_features"], region_features=vis_out["region_features"],
                     decode_tokens=torch.stack(tokens, 1), decode_logits=torch.stack(dec_logits, 1))
     finally:

@@ -95,13 +95,13 @@ def restore(saved):
     sys.modules.update(saved)
 
 
-def case():
+def case(box_score_thres=0.05):
     """Widths the reference hard-codes (box MLP 256, region encoder 256/1024/4096, 64 GN groups) with everything else small."""
     from groma_b200.config import SyntheticTokenizer, tiny_config
     from groma_b200.synth import make_state_dict
     cfg = tiny_config(vit_hidden=64, vit_heads=1, vit_mlp=128, vit_layers=4, d_model=256, ddetr_heads=8, ddetr_ffn=96, enc_layers=2,
                       dec_layers=3, num_queries=40, gn_groups=64, fuse_rounds=5, pos_hidden=256, region_mid=1024, llm_hidden=4096,
-                      llm_heads=32, llm_layers=1, llm_inter=64, vocab=200, max_region_num=12, box_score_thres=0.05, nms_thres=0.6)
+                      llm_heads=32, llm_layers=1, llm_inter=64, vocab=200, max_region_num=12, box_score_thres=box_score_thres, nms_thres=0.6)
     sd = make_state_dict(cfg, seed=21, perturb_norms=True)
     pe = sd["perceiver.vis_encoder.embeddings.position_embeddings"]
     pe[:, 1:] = pe[:, 1:2]                            # constant over the patch grid (see the module docstring)
@@ -120,8 +120,18 @@ def case():
     return cfg, sd, tok, images, ids, refer, ground
 
 
-def run_reference(seed=1234):
-    cfg, sd, tok, images, ids, refer, ground = case()
+def plain_ids(ids, tok):
+    ids = ids.clone()
+    for name in ("<refer_box>", "<refer_feat>", "<ground_box>"):
+        ids[ids == tok.map[name]] = 11
+    return ids
+
+
+def run_reference(seed=1234, box_score_thres=0.05, with_user_boxes=True):
+    cfg, sd, tok, images, ids, refer, ground = case(box_score_thres)
+    if not with_user_boxes:      # plain prompt: no <refer_box>/<refer_feat>/<ground_box>, no user boxes
+        ids = plain_ids(ids, tok)
+        refer = ground = None
     import transformers as tr
     from groma.model.groma import _ddetr_cfg as shim_ddetr_cfg     # the repo's helper: builds a DeformableDetrConfig offline
     dc = shim_ddetr_cfg(cfg)
@@ -157,7 +167,8 @@ def run_reference(seed=1234):
         ids_in = ids.clone()
         torch.manual_seed(seed)
         with torch.no_grad():
-            out = m(input_ids=ids_in, images=images, refer_boxes=[r.clone() for r in refer], ground_boxes=[g.clone() for g in ground],
+            out = m(input_ids=ids_in, images=images, refer_boxes=[r.clone() for r in refer] if refer is not None else None,
+                    ground_boxes=[g.clone() for g in ground] if ground is not None else None,
                     labels=ids.clone(), use_cache=True, return_dict=True)
             # decode branch (groma.py:376-379): the reference reads `past_key_values[0][0].shape`, i.e. 4.32's tuple cache; give
             # the 5.x cache object that one accessor, nothing else
@@ -189,6 +200,10 @@ if __name__ == "__main__":
     keep["image_features"] = out["image_features"][:, ::16, ::16].clone()
     keep["region_features"] = out["region_features"][:, ::16].clone()
     keep["decode_logits"] = out["decode_logits"][:, :, ::7].clone()
+    # second scenario: score threshold above every proposal score -> NMS returns nothing -> argmax-box fallback (groma.py:276-278)
+    fb = run_reference(box_score_thres=0.9999, with_user_boxes=False)
+    keep["fallback"] = dict(selected_boxes=fb["selected_boxes"], logits=fb["logits"][:, :, ::7].clone(), loss=fb["loss"],
+                            decode_tokens=fb["decode_tokens"])
     torch.save({"outputs": keep, "note": "reference GromaModel.forward (prefill) outputs on case(); see this script"},
                os.path.join(HERE, "groma_forward_ref.pt"))
-    print("wrote groma_forward_ref.pt", {k: (tuple(v.shape) if torch.is_tensor(v) else [tuple(x.shape) for x in v]) for k, v in keep.items()})
+    print("wrote groma_forward_ref.pt", {k: tuple(v.shape) for k, v in keep.items() if torch.is_tensor(v)}, "fallback T =", keep["fallback"]["logits"].shape[1])

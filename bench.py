@@ -36,6 +36,8 @@ def parse_args():
     ap.add_argument("--prompt", type=int, default=512)
     ap.add_argument("--new", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-check", action="store_true",
+                    help="skip the full-size GPU-vs-oracle parity check that rides in the JSON line as `parity_check` (N=1 only)")
     ap.add_argument("--tiny", action="store_true", help="debug: miniature model")
     ap.add_argument("--profile", action="store_true", help="print a per-stage CUDA-event breakdown of one step to stderr")
     ap.add_argument("--ncu-range", action="store_true",
@@ -290,9 +292,28 @@ def main():
         sd_cpu = {k: v.float().cpu() for k, v in sd_for_cpu.items()}
         del sd_for_cpu
         line["cpu_baseline"] = cpu_reference(cfg, tok, args.prompt, args.new, sd_cpu)
+        if not args.no_check:
+            line["parity_check"] = parity_check(model, cfg, sd_cpu, tok, args)
     else:
         line["cpu_baseline"] = None
     print(json.dumps(line))
+
+
+def parity_check(model, cfg, sd_cpu, tok, args):
+    """Not timed, not part of `value`: the SAME weights the timed steps ran on, one image + one prompt of the benchmark's
+    length through the GPU path and through the CPU oracle (the checker), stage by stage -- tests/fullsize.py.  Keys:
+    every `*_nrel` / `*_max_abs` distance, the exactness flags of the integer stages, `violations` (bars of
+    tests/test_fullsize_gpu.py that are not met; empty = green)."""
+    try:
+        from tests.fullsize import BARS, run_fullsize_check, verdict
+        res = run_fullsize_check(model, cfg, sd_cpu, tok, n_text=args.prompt, n_new=8, log=lambda m: print(m, file=sys.stderr))
+        res["violations"] = verdict(res)
+        res["bars"] = BARS
+        return res
+    except Exception as e:   # the benchmark line must survive a checker failure
+        import traceback
+        traceback.print_exc(file=sys.stderr)
+        return {"error": f"{type(e).__name__}: {e}"}
 
 
 def decode_gemm_roofline(model, B, args, step):

@@ -120,11 +120,29 @@ class GenerateOutput:
     past_key_values: Optional[Tuple] = None
 
 
-@dataclass
-class _GenConfig:
-    eos_token_id: Optional[int] = None
-    pad_token_id: Optional[int] = None
-    max_new_tokens: int = 20
+def _load_generation_config(path: Optional[str], config: "GromaConfig"):
+    """`model.generation_config` as the reference's checkpoints carry it: train.py:108-112 stores the tokenizer's
+    eos / pad / bos ids in `generation_config.json`, and every eval script passes it back to generate()
+    (eval/run_groma.py:92).  Falls back to the ids in config.json (top level, then llm_cfg) when the file is absent."""
+    from transformers import GenerationConfig
+    if path is not None and os.path.isfile(os.path.join(path, "generation_config.json")):
+        return GenerationConfig.from_pretrained(path)
+    l = config.llm_cfg
+
+    def pick(name):
+        v = config.__dict__.get(name)
+        return v if v is not None else getattr(l, name, None)
+    return GenerationConfig(eos_token_id=pick("eos_token_id"), pad_token_id=pick("pad_token_id"), bos_token_id=pick("bos_token_id"))
+
+
+def _eos_list(eos) -> List[int]:
+    if eos is None:
+        return []
+    if isinstance(eos, torch.Tensor):
+        return [int(v) for v in eos.reshape(-1).tolist()]
+    if isinstance(eos, (list, tuple)):
+        return [int(v) for v in eos]
+    return [int(eos)]
 
 
 def _c2c(b: torch.Tensor) -> torch.Tensor:
@@ -154,7 +172,7 @@ class GromaModel(torch.nn.Module):
         self._path_cfg = path_config if path_config is not None else config.to_path_config(image_size)
         self.engine = GromaEngine(self._path_cfg, state_dict)
         self.perceiver = CustomDDETRModel(config.perceiver_cfg, engine=self.engine)
-        self.generation_config = _GenConfig()
+        self.generation_config = _load_generation_config(None, config)
         self.pad_token_id = None
         self.img_token_id = None
         self.reg_token_id = None
@@ -163,6 +181,7 @@ class GromaModel(torch.nn.Module):
         self.ground_box_token_id = None
         self.box_idx_token_ids = None
         self.use_cuda_graph = True
+        self.kv_headroom = 64      # decode positions reserved by forward(use_cache=True) beyond the prompt (grows on demand)
         self._graph = None
         self.profile = None   # set to a list to collect (stage name, cuda event) marks during generate()
 
@@ -174,13 +193,19 @@ class GromaModel(torch.nn.Module):
 
     # ------------------------------------------------------------------ loading (HF checkpoint layout)
     @classmethod
-    def from_pretrained(cls, path: str, torch_dtype=None, **kwargs) -> "GromaModel":
-        if kwargs.get("load_in_8bit") or kwargs.get("quantization_config") is not None:
+    def from_pretrained(cls, path: str, *model_args, torch_dtype=None, config=None, **kwargs) -> "GromaModel":
+        """`GromaModel.from_pretrained(dir)` (eval/run_groma.py:43-61) and `AutoModel.from_pretrained(dir)` (which resolves
+        GromaConfig -> GromaModel through the registration at the bottom of this file and passes `config=`).  torch_dtype is
+        accepted and ignored: the arithmetic type of the path is bf16 with fp32 accumulation (== the autocast region the
+        reference's callers wrap generate() in)."""
+        if kwargs.get("load_in_8bit") or kwargs.get("load_in_4bit") or kwargs.get("quantization_config") is not None:
             raise NotImplementedError("8/4-bit loading would change results; the B200 path is bf16")
         from groma_b200.checkpoint import ShardedStateDict, load_config_dict
+        path = os.path.expanduser(str(path))
         cd = load_config_dict(path)
         cd.pop("model_type", None)
-        config = GromaConfig(**cd)
+        if not isinstance(config, GromaConfig):
+            config = GromaConfig(**cd)
         # lazy view over the (sharded) checkpoint: the engine packs tensor by tensor into its bf16 device arena
         view = ShardedStateDict(path)
         # region-encoder widths are code constants in the reference (roi_align.py:97-116,233-271), not config fields:
@@ -190,7 +215,9 @@ class GromaModel(torch.nn.Module):
                     pos_hidden=view.shape(re_ + "roi_align.pos_embedd.0.weight")[0],
                     fuse_rounds=sum(1 for k in view if k.startswith(re_ + "mlvl_fuse.fuse_convs.") and k.endswith(".conv.weight")))
         geom.update(cd.get("path_overrides") or {})     # e.g. {"gn_groups": 8} for miniature test checkpoints (reference: 64)
-        return cls(config, state_dict=view, path_config=config.to_path_config(**geom))
+        model = cls(config, state_dict=view, path_config=config.to_path_config(**geom))
+        model.generation_config = _load_generation_config(path, config)
+        return model
 
     def cuda(self, device=None):
         return self
@@ -334,15 +361,21 @@ class GromaModel(torch.nn.Module):
             x, ids_new, labels_new, mask, vis_outputs, aux = self._prefill_inputs(input_ids, images, refer_boxes, ground_boxes, labels,
                                                                                   _selected_override)
             B, T = ids_new.shape
-            eng.alloc_kv(B, T + max(int(_reserve), 1))
+            eng.ensure_rope(T + 1)
+            # room for a step-wise decode loop over forward(past_key_values=...) (serve/model_worker.py:288-304, serve/cli.py
+            # and HF generate all drive the model that way); the cache grows geometrically beyond it
+            eng.alloc_kv(B, T + max(int(_reserve), self.kv_headroom))
             kv_len = mask.sum(1).to(torch.int32).to(eng.dev)
             logits = eng.llm_prefill(x, B, T, kv_len).reshape(B, T, -1)
             self._last = dict(ids=ids_new, mask=mask, aux=aux)
         else:
             B = past_key_values[0][0].shape[0]
             past = past_key_values[0][0].shape[-2]
-            if eng.kv is None or past != eng.past or past + 1 > eng.kv_cap:
+            if eng.kv is None or past != eng.past or B != eng.kv.shape[2]:
                 raise RuntimeError("past_key_values must be the cache returned by the previous forward() of this model")
+            if past + 1 > eng.kv_cap:
+                eng.grow_kv(max(past + 1, 2 * eng.kv_cap))      # new storage: the captured decode graph is keyed on it
+            eng.ensure_rope(past + 1)
             d = eng._decode_buffers(B)
             d["ids"].copy_(input_ids.reshape(-1).to(eng.dev))
             d["pos"].fill_(past)
@@ -373,14 +406,16 @@ class GromaModel(torch.nn.Module):
         gc = generation_config or self.generation_config
         if max_new_tokens is None:
             max_new_tokens = getattr(gc, "max_new_tokens", None) or 20
-        if eos_token_id is None:
-            eos_token_id = getattr(gc, "eos_token_id", None)
+        eos_ids = _eos_list(eos_token_id if eos_token_id is not None else getattr(gc, "eos_token_id", None))
+        pad_id = getattr(gc, "pad_token_id", None)
         eng = self.engine
         dev = eng.dev
         x, ids_new, _, mask, vis_outputs, aux = self._prefill_inputs(input_ids, images, refer_boxes, ground_boxes, None, _selected_override)
         B, T = ids_new.shape
+        eng.ensure_rope(T + max_new_tokens)        # HF's rotary cache extends on demand; ours is rebuilt before the kernels index it
         eng.alloc_kv(B, T + max_new_tokens)
         kv_len = mask.sum(1).to(torch.int32).to(dev)
+        self._last = dict(ids=ids_new, mask=mask, aux=aux)
         self._mark("assemble+embed")
         logits = eng.llm_prefill(x, B, T, kv_len, last_only=True)          # [B, V] at the last (padded) position
         self._mark("llm_prefill")
@@ -391,10 +426,15 @@ class GromaModel(torch.nn.Module):
         out_tokens = torch.empty((max_new_tokens, B), dtype=torch.int64, device=dev)
         out_tokens[0].copy_(d["ids"])
         self._step_logits = [logits.clone()] if kwargs.get("_keep_logits") else None
+        eos_t = torch.tensor(eos_ids, dtype=torch.int64, device=dev) if eos_ids else None
         graph = None
         steps_done = 1
         check_every = 16
         for s in range(1, max_new_tokens):
+            if eos_t is not None and (s == 1 or s % check_every == 0):
+                # one host sync every `check_every` steps: stop once every row has produced an EOS
+                if bool(torch.isin(out_tokens[:steps_done], eos_t).any(0).all()):
+                    break
             if self.use_cuda_graph and graph is None and s >= 2:
                 graph = self._capture(B)
             if graph is not None:
@@ -405,18 +445,17 @@ class GromaModel(torch.nn.Module):
             if self._step_logits is not None:
                 self._step_logits.append(d["logits"].clone())
             steps_done = s + 1
-            if eos_token_id is not None and (s % check_every == 0):
-                if bool((out_tokens[:steps_done] == eos_token_id).any(0).all()):
-                    break
         self._mark("decode")
         eng.past = T + steps_done - 1
         new = out_tokens[:steps_done].t().contiguous()
-        if eos_token_id is not None:
-            # HF semantics: a finished row is padded; generation stops once every row has finished
-            is_eos = new == eos_token_id
+        if eos_t is not None:
+            # HF greedy_search semantics: a row that has emitted EOS is fed / reported as pad_token_id from then on, and
+            # generation ends with the step at which the last unfinished row emits its EOS
+            if pad_id is None:
+                pad_id = self.pad_token_id if self.pad_token_id is not None else eos_ids[0]
+            is_eos = torch.isin(new, eos_t)
             after = (is_eos.cumsum(1) - is_eos.long()) > 0
-            pad = self.pad_token_id if self.pad_token_id is not None else eos_token_id
-            new = torch.where(after, torch.full_like(new, pad), new)
+            new = torch.where(after, torch.full_like(new, pad_id), new)
             finished_at = torch.where(is_eos.any(1), is_eos.float().argmax(1) + 1, torch.full((B,), new.shape[1], device=dev))
             new = new[:, :int(finished_at.max())]
         sequences = torch.cat([input_ids.to(dev), new], 1)
@@ -428,7 +467,7 @@ class GromaModel(torch.nn.Module):
     def _capture(self, B: int):
         """Capture one decode step (all 32 layers + heads + argmax + position advance) into a CUDA graph."""
         eng = self.engine
-        key = (B, eng.kv.data_ptr(), eng.kv_cap)
+        key = (B, eng.kv.data_ptr(), eng.kv_cap, eng.rope_cos.data_ptr())
         if self._graph is not None and self._graph[0] == key:
             return self._graph[1]
         g = torch.cuda.CUDAGraph()

@@ -276,6 +276,9 @@ __global__ void __cluster_dims__(DEC_SPLIT, 1, 1) __launch_bounds__(DEC_WARPS * 
     __nv_bfloat16* __restrict__ out, const int* __restrict__ kv_len, int H, long long cap, float scale_log2) {
     static_assert(D == 128, "16 lanes x 8 dims");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // distributed-shared-memory rule: a CTA may only touch a peer's shared memory once that peer is known to be running.
+    // Arrive now, wait just before the first remote store -- the barrier latency hides behind the key loop.
+    cluster_arrive_relaxed();
     asm volatile("griddepcontrol.wait;" ::: "memory");   // no-op unless launched with programmatic serialisation
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -374,6 +377,7 @@ __global__ void __cluster_dims__(DEC_SPLIT, 1, 1) __launch_bounds__(DEC_WARPS * 
 #pragma unroll
     for (int t = 0; t < 8; ++t) sm_acc[slot][l * 8 + t] = acc[t];
     __syncthreads();
+    cluster_wait();   // pairs with the arrive at kernel entry: every CTA of the cluster has started
     // CTA-level merge -> (M, den, num[D]) sent to the leader CTA's shared memory (distributed shared memory)
     float* r_m = cluster.map_shared_rank(peer_m, 0);
     float* r_l = cluster.map_shared_rank(peer_l, 0);
@@ -447,6 +451,7 @@ __global__ void __cluster_dims__(DEC_SPLIT, 1, 1) __launch_bounds__((DEC_WARPS +
     __shared__ float sm_m[DEC_WARPS * 2], sm_l[DEC_WARPS * 2], sm_acc[DEC_WARPS * 2][D];
     __shared__ float peer_m[DEC_SPLIT], peer_l[DEC_SPLIT], peer_acc[DEC_SPLIT][D];
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    cluster_arrive_relaxed();   // see decode_attention_kernel: waited on right before the first remote shared-memory store
     if (threadIdx.x == 0) {
         for (int s = 0; s < DT_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], DEC_WARPS); }
         fence_barrier_init();
@@ -591,6 +596,7 @@ __global__ void __cluster_dims__(DEC_SPLIT, 1, 1) __launch_bounds__((DEC_WARPS +
         for (int t = 0; t < 8; ++t) sm_acc[slot][l * 8 + t] = acc[t];
     }
     __syncthreads();
+    cluster_wait();
     float* r_m = cluster.map_shared_rank(peer_m, 0);
     float* r_l = cluster.map_shared_rank(peer_l, 0);
     float* r_acc = cluster.map_shared_rank(&peer_acc[0][0], 0);

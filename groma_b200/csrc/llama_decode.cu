@@ -82,6 +82,7 @@ __global__ void __cluster_dims__(RN_CL, 1, 1) __launch_bounds__(128)
 reduce_residual_rmsnorm_cluster_kernel(const float* __restrict__ ws, int S, int B, int N, __nv_bfloat16* __restrict__ x,
                                        const float* __restrict__ w, __nv_bfloat16* __restrict__ y, float eps) {
     pdl_trigger();
+    cluster_arrive_relaxed();   // DSMEM rule: peers must be running before their shared memory is written (waited on below)
     pdl_wait();
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -107,6 +108,7 @@ reduce_residual_rmsnorm_cluster_kernel(const float* __restrict__ ws, int S, int 
         *reinterpret_cast<uint2*>(xp) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
     }
     const float ss_local = block_sum_f(act ? (h0 * h0 + h1 * h1 + h2 * h2 + h3 * h3) : 0.f, red);
+    cluster_wait();
     if (threadIdx.x < RN_CL) {
         float* peer = cluster.map_shared_rank(part, threadIdx.x);
         peer[crank] = ss_local;                  // every CTA publishes its slice sum to all peers

@@ -173,6 +173,9 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// split cluster barrier: arrive early (no memory ordering needed, it only proves "this CTA is running"), wait late
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
 // TMA load issued by either CTA of a pair; the transaction bytes are credited to the LEADER CTA's mbarrier (the barrier's
 // shared::cluster address with the peer bit cleared names CTA 0's copy of the same offset).
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* d, uint64_t* bar, int32_t c0, int32_t c1) {

@@ -51,6 +51,7 @@ class GromaEngine:
         self.fused_decode = True     # fused reduce epilogues + PDL in the decode step
         self.fused_rope_attn = os.environ.get("GROMA_FUSED_ROPE_ATTN", "1") == "1"   # qkv reduce + RoPE + KV append inside the attention launch
         self.use_pdl = True
+        self.topk_override = None  # tests: int64 [B, num_queries] token indices replacing the proposer's own top-k
         self.timing_hook = None   # bench.py: list collecting (start_event, end_event, algorithmic_bytes) per swap-AB GEMM
 
     # ------------------------------------------------------------------------------------------ weights
@@ -206,10 +207,24 @@ class GromaEngine:
         self.coord = {}
         for s in (g * 4, g * 2, g):
             self.coord[s] = torch.linspace(-1, 1, s).to(self.dev)
+        self.rope_len = 0
+        self.ensure_rope(cfg.max_pos)
+
+    def ensure_rope(self, n: int):
+        """cos/sin tables [n, head_dim/2] for positions < n.  Built for max_position_embeddings at load; a longer sequence
+        rebuilds them (HF's LlamaRotaryEmbedding extends its cache the same way, $HF/models/llama/modeling_llama.py:96-113 in
+        4.32) instead of letting rope_kv / the decode kernels index past the end.  New storage invalidates captured graphs
+        (the capture key in GromaModel._capture includes the table pointer)."""
+        if n <= self.rope_len:
+            return
+        cfg = self.cfg
         hd = cfg.head_dim
+        n = max(n, cfg.max_pos, 2 * self.rope_len)
         inv = 1.0 / (cfg.rope_theta ** (torch.arange(0, hd, 2).float() / hd))
-        fr = torch.outer(torch.arange(cfg.max_pos).float(), inv)
-        self.rope_cos, self.rope_sin = fr.cos().to(self.dev).contiguous(), fr.sin().to(self.dev).contiguous()
+        fr = torch.outer(torch.arange(n).float(), inv)
+        with torch.inference_mode(False):
+            self.rope_cos, self.rope_sin = fr.cos().to(self.dev).contiguous(), fr.sin().to(self.dev).contiguous()
+        self.rope_len = n
 
     def _stage(self, name, t):
         if self.keep_stages:
@@ -295,6 +310,11 @@ class GromaEngine:
         t = G.gemm(t, w[f"bbox.{L}.1.w"], bias=w[f"bbox.{L}.1.b"], act=G.ACT_RELU)
         delta = G.gemm(t, w[f"bbox.{L}.2.w"], bias=w[f"bbox.{L}.2.b"], out_f32=True).reshape(B, S, 4)
         topk = G.topk_desc(cls, Qn)
+        self._stage("topk_own", topk)
+        if self.topk_override is not None:
+            # parity tests only: continue with the oracle's query selection so that everything downstream of the (tie-sensitive)
+            # two-stage top-k is comparable query by query; the engine's own selection is kept in stages['topk_own']
+            topk = self.topk_override.to(self.dev, torch.int64).contiguous()
         ref, pos512 = G.ddetr_select(delta, self.prop_logit, topk, D // 2)
         self._stage("enc_cls", cls); self._stage("topk", topk); self._stage("ref_init", ref)
         pt = G.layernorm(G.gemm(pos512.reshape(B * Qn, 2 * D), w["pos_trans.w"], bias=w["pos_trans.b"]),
@@ -440,8 +460,21 @@ class GromaEngine:
         cfg = self.cfg
         shape = (cfg.llm_layers, 2, B, cfg.llm_heads, cap, cfg.head_dim)
         if self.kv is None or tuple(self.kv.shape) != shape:
-            self.kv = torch.zeros(shape, dtype=torch.bfloat16, device=self.dev)
+            self.kv = None
+            # persistent buffers are ordinary tensors even when the caller runs under torch.inference_mode()
+            # (eval/run_groma.py:81): later calls outside it update them in place
+            with torch.inference_mode(False):
+                self.kv = torch.zeros(shape, dtype=torch.bfloat16, device=self.dev)
         self.kv_cap = cap
+
+    def grow_kv(self, cap: int):
+        """Re-home the cache with room for `cap` positions, keeping the first `past` of every (layer, k/v, row, head)."""
+        old, past = self.kv, self.past
+        L, _, B, H, _, D = old.shape
+        with torch.inference_mode(False):
+            new = torch.zeros((L, 2, B, H, cap, D), dtype=torch.bfloat16, device=self.dev)
+        new[:, :, :, :, :past].copy_(old[:, :, :, :, :past])
+        self.kv, self.kv_cap = new, cap
 
     def llm_prefill(self, x: torch.Tensor, B: int, T: int, kv_len: torch.Tensor, last_only: bool = False) -> torch.Tensor:
         """$HF/models/llama/modeling_llama.py LlamaModel forward (32 x LlamaDecoderLayer :292-340) + both heads
@@ -476,6 +509,12 @@ class GromaEngine:
         key = (B,)
         if getattr(self, "_dbuf_key", None) == key:
             return self._dbuf
+        with torch.inference_mode(False):
+            d = self._new_decode_buffers(B, Hd, I, V)
+        self._dbuf, self._dbuf_key = d, key
+        return d
+
+    def _new_decode_buffers(self, B, Hd, I, V):
         d = dict(
             ids=torch.zeros((B,), dtype=torch.int64, device=self.dev),
             x=torch.empty((B, Hd), dtype=torch.bfloat16, device=self.dev),
@@ -490,7 +529,6 @@ class GromaEngine:
             cnt=torch.zeros((1024,), dtype=torch.int32, device=self.dev),   # split-K tile counters (self re-arming)
             kv_len=torch.zeros((B,), dtype=torch.int32, device=self.dev),
         )
-        self._dbuf, self._dbuf_key = d, key
         return d
 
     def _decode_splits(self):

@@ -37,14 +37,18 @@ def _bf(x: torch.Tensor) -> torch.Tensor:
 
 
 class Oracle:
-    def __init__(self, cfg: PathConfig, sd: Dict[str, torch.Tensor], prec: str = "bf16"):
+    def __init__(self, cfg: PathConfig, sd: Dict[str, torch.Tensor], prec: str = "bf16", prerounded: bool = False):
+        """prerounded: `sd` holds fp32 tensors whose matrices already carry bf16-representable values (e.g. the bf16 arena of
+        the GPU model copied back and widened): used as they are, so a 'bf16' and an 'fp32' oracle of Groma-7B size can share
+        one 30 GB dict."""
         assert prec in ("fp32", "bf16")
         self.cfg = cfg
         self.prec = prec
         self.r = _bf if prec == "bf16" else (lambda x: x)
         # matrices (dim >= 2) are stored in bf16 on the device; vectors (bias / norm / LayerScale) stay fp32
         # (v.float() is a no-op view for fp32 inputs, so the 7B-size fp32 oracle does not duplicate its 30 GB of weights)
-        self.sd = {k: (self.r(v.float()) if v.dim() >= 2 else v.float()) for k, v in sd.items()}
+        rm = (lambda x: x) if prerounded else self.r
+        self.sd = {k: (rm(v.float()) if v.dim() >= 2 else v.float()) for k, v in sd.items()}
         self.tok = None
         self.stages: Dict[str, torch.Tensor] = {}
 
@@ -265,6 +269,25 @@ class Oracle:
                                 query_pos=query_pos, tgt=r(self.W(dt + "query_position_embeddings.weight"))[None].expand(B, -1, -1)))
         return pred, scores, {"coco": coco, "sa1b": sa1b}
 
+    # ------------------------------------------------------------------ N1: detector post-processing (train/train_det.py:97-131)
+    @staticmethod
+    def post_process(coco_logits, pred_boxes, target_sizes, threshold=0.0, top_k=100):
+        """coco_logits [B,Q,C], pred_boxes [B,Q,4] cxcywh in (0,1), target_sizes [B,2] (h, w).  torch.topk's order among
+        equal values is unspecified; the restatement takes them by lower flat index (stable argsort)."""
+        B, Q, C = coco_logits.shape
+        prob = coco_logits.float().sigmoid().reshape(B, -1)
+        k = min(top_k, prob.shape[1])
+        idx = torch.stack([torch.from_numpy(np.argsort(-prob[b].numpy(), kind="stable")[:k].copy()) for b in range(B)])
+        scores = torch.gather(prob, 1, idx)
+        qi, labels = torch.div(idx, C, rounding_mode="floor"), idx % C
+        bx = pred_boxes.float()
+        xyxy = torch.cat([bx[..., :2] - 0.5 * bx[..., 2:], bx[..., :2] + 0.5 * bx[..., 2:]], -1)
+        xyxy = torch.gather(xyxy, 1, qi[..., None].repeat(1, 1, 4))
+        ts = torch.as_tensor(target_sizes, dtype=torch.float32)
+        img_h, img_w = ts.unbind(1)
+        xyxy = xyxy * torch.stack([img_w, img_h, img_w, img_h], 1)[:, None, :]
+        return [{"scores": s[s > threshold], "labels": l[s > threshold], "boxes": b[s > threshold]} for s, l, b in zip(scores, labels, xyxy)]
+
     # ------------------------------------------------------------------ a10: region selection (groma.py:251-280)
     def select_regions(self, pred_boxes, scores, refer_boxes=None, ground_boxes=None, rng_draw=True):
         cfg = self.cfg
@@ -475,6 +498,7 @@ class Oracle:
         assert self.tok is not None
         hs = self.vit(images)
         self.stages["vit_last"] = hs[-1]
+        self.stages["vit_hs"] = hs[-4:]
         img_tok = self.image_tokens(hs[-1])
         pred, scores, logits = self.proposer(hs)
         if selected_override is not None:

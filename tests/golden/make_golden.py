@@ -34,7 +34,7 @@ def run_oracle():
     out = o.generate(ids.clone(), images, 5)
     return dict(input_ids=out["input_ids"], new_tokens=out["new_tokens"], nms_inds=[torch.from_numpy(x) for x in out["nms_inds"]],
                 pred_boxes=out["pred_boxes"], scores=out["scores"], selected_boxes=out["selected_boxes"],
-                last_logits=out["logits"][:, -1].clone(), step_logits=out["step_logits"])
+                last_logits=out["logits"][:, -1].clone(), step_logits=out["step_logits"], topk=o.stages["topk"].clone())
 
 
 if __name__ == "__main__":

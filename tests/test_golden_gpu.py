@@ -40,8 +40,25 @@ def test_gpu_reproduces_golden_fixture():
                 top2 = sl[b, t].topk(2).values
                 assert (top2[0] - top2[1]) < 1e-2 * sl[b, t].abs().max(), f"row {b} step {t} diverged with a clear margin"
                 break
-    # detector outputs: fp32 boxes/scores of the 60 proposals, compared where the two-stage top-k picked the same tokens
+    # detector outputs: fp32 boxes/scores of the 60 proposals.  The two-stage top-k is tie-sensitive, so the decoder is fed the
+    # fixture's query selection (engine.topk_override) and the boxes / scores are asserted slot by slot; the GPU's own
+    # selection must agree with the fixture's on (nearly) all tokens
     hs = m.engine.vit(images.cuda())
-    pc, _, sc, _ = m.engine.proposer(hs)
-    d = (pc.cpu()[:, :cfg.num_queries] - gold["pred_boxes"]).abs().max().item()
-    print(f"pred_boxes max abs diff vs fixture {d:.3e} (top-k ordering is tie-sensitive)")
+    m.engine.keep_stages = True
+    m.engine.topk_override = gold["topk"]
+    pc, px, sc, _ = m.engine.proposer(hs)
+    m.engine.topk_override = None
+    Q = cfg.num_queries
+    own = m.engine.stages["topk_own"].cpu()
+    overlap = sum(len(set(own[b].tolist()) & set(gold["topk"][b].tolist())) for b in range(2)) / (2 * Q)
+    d = (pc.cpu()[:, :Q] - gold["pred_boxes"]).abs().max().item()
+    ds = (sc.cpu()[:, :Q] - gold["scores"]).abs().max().item()
+    print(f"pred_boxes max abs diff vs fixture {d:.3e}, scores {ds:.3e}, own top-k overlap {overlap:.3f}")
+    assert d < 5e-3 and ds < 5e-3 and overlap > 0.9
+    # region selection on those proposals: keep list equal to the fixture's (score gaps / IoUs of this fixture are far from ties)
+    torch.manual_seed(99)
+    sel = m.engine.select_regions(pc.clone(), px.clone(), sc.clone(), None, None, cfg.nms_thres, cfg.box_score_thres, cfg.max_region_num)
+    keep, num = m.engine.stages["nms_keep"], m.engine.stages["nms_num"]
+    for b in range(2):
+        assert keep[b, :int(num[b])].tolist() == gold["nms_inds"][b].tolist()
+        assert torch.allclose(sel[b], gold["selected_boxes"][b], rtol=0, atol=5e-3)      # same boxes in the same randperm order

@@ -74,11 +74,19 @@ def test_proposer_and_selection(setup):
     same_topk = (st["topk"].cpu() == o.stages["topk"]).float().mean().item()
     print(f"topk identical fraction {same_topk:.3f}; enc_cls max abs diff {(st['enc_cls'].cpu() - o.stages['enc_cls']).abs().max():.2e}")
     assert nrel(st["memory"], o.stages["memory"]) < 1.5e-2 and rmsrel(st["memory"], o.stages["memory"]) < 6e-3
-    if same_topk == 1.0:
-        dbox = (pc.cpu()[:, :cfg.num_queries] - pred_o).abs().max().item()
-        dsc = (sc.cpu()[:, :cfg.num_queries] - sc_o).abs().max().item()
-        print(f"pred_boxes max abs diff {dbox:.2e}, scores max abs diff {dsc:.2e}")
-        assert dbox < 2e-2 and dsc < 2e-2
+    # the GPU's top-k is exactly the stable descending order of ITS objectness scores; boxes / scores are then asserted with
+    # the oracle's query selection teacher-forced (the boundary of a 60-of-1024 top-k on random-init scores can sit in a near-tie)
+    cls_g = st["enc_cls"].cpu()
+    for b in range(cls_g.shape[0]):
+        assert st["topk"][b].tolist() == torch.argsort(-cls_g[b], stable=True)[:cfg.num_queries].tolist()
+    assert same_topk > 0.9
+    m.engine.topk_override = o.stages["topk"]
+    pc_t, _, sc_t, _ = m.engine.proposer(hs_g)
+    m.engine.topk_override = None
+    dbox = (pc_t.cpu()[:, :cfg.num_queries] - pred_o).abs().max().item()
+    dsc = (sc_t.cpu()[:, :cfg.num_queries] - sc_o).abs().max().item()
+    print(f"pred_boxes max abs diff {dbox:.2e}, scores max abs diff {dsc:.2e}")
+    assert dbox < 5e-3 and dsc < 5e-3
     # selection: same boxes/scores in -> identical keep indices and identical shuffled boxes (same CPU RNG seed)
     torch.manual_seed(123)
     sel_g = m.engine.select_regions(pc.clone(), px.clone(), sc.clone(), None, None, cfg.nms_thres, cfg.box_score_thres, cfg.max_region_num)

@@ -1,19 +1,27 @@
-// Flash-attention forward on the 5th-generation tensor cores (sm_100a): S = Q K^T and O = P V are tcgen05.mma with fp32
-// accumulators in TMEM; Q/K/V tiles arrive by TMA (128B swizzle); the softmax runs on 128 threads (one query row per TMEM
-// lane), writes P as bf16 straight into the swizzled shared-memory operand layout, and keeps the running output in
-// registers (rescaled once per KV tile).  Replaces the mma.sync kernel for head dims 64 (DINOv2) and 128 (LLaMA prefill):
+// Flash-attention forward on the 5th-generation tensor cores (sm_100a) for head dims 64 (DINOv2, Deformable-DETR is 32 and
+// stays on the small kernel) and 128 (LLaMA prefill):
 //   $HF/models/llama/modeling_llama.py:199-289 (causal + key-padding), $HF/models/dinov2/modeling_dinov2.py:153-179.
 //
-// CTA = 192 threads: warp 0 TMA producer, warp 1 MMA issuer (one thread), warps 2-5 softmax / output.
-// Per KV tile j (128 keys):   QK_j -> [softmax_j: 2 passes over S in TMEM, P_j -> smem] -> PV_j -> O_j added in registers,
-// with QK_{j+1} issued right behind PV_j so the tensor pipe works while the softmax warps fold O_j.
-// V is consumed in its natural [key][d] layout as an MN-major B operand (no transpose pass).
+// One CTA = TWO 128-row query tiles (A, B) of one (batch, head) in ping-pong over the same K/V stream:
+//   warp 0        TMA producer: Q_A, Q_B once, then K_j / V_j tiles of 128 keys into separate 2-deep rings
+//                 (warps 0-3 form one warpgroup that hands its registers to the softmax warpgroups with setmaxnreg)
+//   warp 1        one thread issues every tcgen05.mma:  S_X = Q_X K_j^T (operands in shared memory), O_X += P_X V_j with
+//                 P_X read straight from TENSOR MEMORY (it overwrites the first 64 columns of S_X as packed bf16) and V
+//                 consumed in its natural [key][d] layout as an MN-major B operand
+//   warps 4-7     softmax of tile A, warps 8-11 softmax of tile B: thread = query row = TMEM lane; ONE pass over the 128 scores
+//                 of the row held in registers (max, exp2, row sum, bf16 pack, tcgen05.st)
+// Issue order  QK_A(j+1) right behind PV_A(j), QK_B(j+1) behind PV_B(j): while the softmax warps of one tile work, the tensor
+// pipe runs the other tile's PV and next QK.  The running output stays in TMEM (fp32, accumulated by the MMA); it is only
+// touched by the softmax warps when the running row maximum has grown by more than 2^8 since the value the exponentials are
+// currently referenced to (then O and the row sum are rescaled once) and at the end (O / l -> bf16).  Everything else --
+// masks, scale, log2(e) folding -- is one FFMA + MUFU.EX2 per score.
+// TMEM: S_A [0,128) S_B [128,256) O_A [256,256+D) O_B [384,384+D) = all 512 columns, one CTA per SM.
 #include "ptx.cuh"
 #include "capi_common.h"
 
 namespace gb {
 
-constexpr int FA_BM = 128, FA_BN = 128, FA_THREADS = 192, FA_KV_STAGES = 2;
+constexpr int FA_BM = 128, FA_BN = 128, FA_THREADS = 384, FA_STAGES = 2;
 
 struct FaParams {
     CUtensorMap tma_q, tma_k, tma_v;        // 2D [rows, cols] bf16, box {64, 128}
@@ -40,37 +48,80 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr, uint32_t
 __host__ __device__ constexpr uint32_t make_idesc_bf16_ex(uint32_t m, uint32_t n, uint32_t b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (b_mn_major << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (P, bf16 pairs packed in 32-bit columns, row = lane) comes from TMEM
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+        "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
+        "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32_raw(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
 
 template <int D>
-__global__ void __launch_bounds__(FA_THREADS, 1) attention_tcgen05_kernel(const __grid_constant__ FaParams p) {
+struct FaSmem {
+    static constexpr int DBLK = D / 64;                 // 64-column (128-byte) blocks per row of Q/K/V
+    static constexpr int TILE_BYTES = 128 * D * 2;      // one 128-row tile of Q, K or V
+    static constexpr int BYTES = 2 * TILE_BYTES + 2 * FA_STAGES * TILE_BYTES + 1024 + 256;
+};
+
+template <int D>
+__global__ void __launch_bounds__(FA_THREADS, 1) attention_fa2q_kernel(const __grid_constant__ FaParams p) {
     static_assert(D == 64 || D == 128, "head dim");
-    constexpr int DBLK = D / 64;                        // 64-column (128-byte) blocks per row of Q/K/V
-    constexpr int Q_BYTES = FA_BM * D * 2;
-    constexpr int KV_BYTES = FA_BN * D * 2;
-    constexpr int P_BYTES = FA_BM * FA_BN * 2;          // two 64-key blocks of [128 rows][128 B]
-    constexpr int TMEM_COLS = 256;                      // S: cols [0,128), O tile: cols [128, 128+D)
+    using L = FaSmem<D>;
+    constexpr int DBLK = L::DBLK, TILE = L::TILE_BYTES;
     extern __shared__ uint8_t smem_raw_fa[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_fa) + 1023) & ~uintptr_t(1023));
-    uint8_t* Qs = smem;
-    uint8_t* Ks = Qs + Q_BYTES;                         // [stages][KV_BYTES]
-    uint8_t* Vs = Ks + FA_KV_STAGES * KV_BYTES;
-    uint8_t* Ps = Vs + FA_KV_STAGES * KV_BYTES;
-    uint64_t* q_full = reinterpret_cast<uint64_t*>(Ps + P_BYTES);
-    uint64_t* kv_full = q_full + 1;                     // [stages]
-    uint64_t* kv_empty = kv_full + FA_KV_STAGES;        // [stages]
-    uint64_t* s_full = kv_empty + FA_KV_STAGES;
-    uint64_t* p_ready = s_full + 1;
-    uint64_t* o_full = p_ready + 1;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(o_full + 1);
+    uint8_t* Qs = smem;                                 // [2 tiles][DBLK][128 rows][128 B]
+    uint8_t* Ks = Qs + 2 * TILE;                        // [stages][DBLK][128][128 B]
+    uint8_t* Vs = Ks + FA_STAGES * TILE;
+    uint64_t* q_full = reinterpret_cast<uint64_t*>(Vs + FA_STAGES * TILE);
+    uint64_t* k_full = q_full + 1;                      // [stages]
+    uint64_t* k_empty = k_full + FA_STAGES;
+    uint64_t* v_full = k_empty + FA_STAGES;
+    uint64_t* v_empty = v_full + FA_STAGES;
+    uint64_t* s_full = v_empty + FA_STAGES;             // [2 tiles]
+    uint64_t* p_ready = s_full + 2;                     // [2]
+    uint64_t* o_done = p_ready + 2;                     // [2]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(o_done + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-    const int q0 = qb * FA_BM;
+    // heavy (late, for causal) query blocks first: they have the most key tiles
+    const int qb = (int)gridDim.x - 1 - (int)blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int q0 = qb * 2 * FA_BM;
     int sk = p.Sk;
     if (p.kv_len) sk = min(sk, p.kv_len[b]);
-    int k_end = sk;
-    if (p.causal) k_end = min(sk, p.q_pos0 + min(q0 + FA_BM, p.Sq));
-    const int n_tiles = (k_end + FA_BN - 1) / FA_BN;
+    int n_x[2];                                         // key tiles each query tile has to visit
+#pragma unroll
+    for (int X = 0; X < 2; ++X) {
+        const int first = q0 + X * FA_BM;
+        int k_end = sk;
+        if (p.causal) k_end = min(sk, p.q_pos0 + min(first + FA_BM, p.Sq));
+        n_x[X] = (first < p.Sq) ? (k_end + FA_BN - 1) / FA_BN : 0;
+    }
+    const int n_max = max(n_x[0], n_x[1]);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tma_q); tma_prefetch_desc(&p.tma_k); tma_prefetch_desc(&p.tma_v);
@@ -78,168 +129,208 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_tcgen05_kernel(const 
     if (warp == 1) {
         if (lane == 0) {
             mbar_init(q_full, 1);
-            for (int i = 0; i < FA_KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-            mbar_init(s_full, 1);
-            mbar_init(p_ready, 4);
-            mbar_init(o_full, 1);
+            for (int i = 0; i < FA_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_done[i], 1); }
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc<TMEM_COLS>(tmem_holder);
+        tmem_alloc<512>(tmem_holder);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
-    const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
-
+    // register hand-over between warpgroups: the softmax threads keep a whole 128-score row in registers
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;" ::: "memory");
     if (warp == 0) {
-        if (lane == 0 && n_tiles > 0) {
+        if (lane == 0 && n_max > 0) {
             // ---------------- TMA producer
-            mbar_expect_tx(q_full, Q_BYTES);
+            mbar_expect_tx(q_full, 2 * TILE);
 #pragma unroll
-            for (int blk = 0; blk < DBLK; ++blk)
-                tma_load_2d(Qs + blk * (FA_BM * 128), &p.tma_q, q_full, h * p.q_head_cols + blk * 64, b * p.q_batch_rows + q0);
-            for (int j = 0; j < n_tiles; ++j) {
-                const int st = j % FA_KV_STAGES;
-                const uint32_t ph = (j / FA_KV_STAGES) & 1;
-                mbar_wait(&kv_empty[st], ph ^ 1);
-                mbar_expect_tx(&kv_full[st], 2 * KV_BYTES);
+            for (int X = 0; X < 2; ++X)
+#pragma unroll
+                for (int blk = 0; blk < DBLK; ++blk)
+                    tma_load_2d(Qs + X * TILE + blk * (FA_BM * 128), &p.tma_q, q_full, h * p.q_head_cols + blk * 64, b * p.q_batch_rows + q0 + X * FA_BM);
+            for (int j = 0; j < n_max; ++j) {
+                const int st = j % FA_STAGES;
+                const uint32_t ph = (j / FA_STAGES) & 1;
                 const int krow = b * p.k_batch_rows + h * p.k_head_rows + j * FA_BN;
                 const int vrow = b * p.v_batch_rows + h * p.v_head_rows + j * FA_BN;
+                mbar_wait(&k_empty[st], ph ^ 1);
+                mbar_expect_tx(&k_full[st], TILE);
 #pragma unroll
-                for (int blk = 0; blk < DBLK; ++blk) {
-                    tma_load_2d(Ks + st * KV_BYTES + blk * (FA_BN * 128), &p.tma_k, &kv_full[st], h * p.k_head_cols + blk * 64, krow);
-                    tma_load_2d(Vs + st * KV_BYTES + blk * (FA_BN * 128), &p.tma_v, &kv_full[st], h * p.v_head_cols + blk * 64, vrow);
-                }
+                for (int blk = 0; blk < DBLK; ++blk)
+                    tma_load_2d(Ks + st * TILE + blk * (FA_BN * 128), &p.tma_k, &k_full[st], h * p.k_head_cols + blk * 64, krow);
+                mbar_wait(&v_empty[st], ph ^ 1);
+                mbar_expect_tx(&v_full[st], TILE);
+#pragma unroll
+                for (int blk = 0; blk < DBLK; ++blk)
+                    tma_load_2d(Vs + st * TILE + blk * (FA_BN * 128), &p.tma_v, &v_full[st], h * p.v_head_cols + blk * 64, vrow);
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && n_tiles > 0) {
+        if (lane == 0 && n_max > 0) {
             // ---------------- MMA issuer
             constexpr uint32_t idesc_qk = make_idesc_bf16_ex(FA_BM, FA_BN, 0);   // S[128 x 128] = Q (K-major) . K^T (K-major)
-            constexpr uint32_t idesc_pv = make_idesc_bf16_ex(FA_BM, D, 1);       // O[128 x D]   = P (K-major) . V (MN-major)
-            const uint32_t q_addr = smem_u32(Qs), p_addr = smem_u32(Ps);
-            auto issue_qk = [&](int j) {
-                const int st = j % FA_KV_STAGES;
-                mbar_wait(&kv_full[st], (j / FA_KV_STAGES) & 1);
-                tc_fence_after();
-                const uint32_t k_addr = smem_u32(Ks + st * KV_BYTES);
+            constexpr uint32_t idesc_pv = make_idesc_bf16_ex(FA_BM, D, 1);       // O[128 x D]   = P (TMEM)    . V (MN-major)
+            auto issue_qk = [&](int X, int j) {
+                const int st = j % FA_STAGES;
+                const uint32_t q_addr = smem_u32(Qs + X * TILE), k_addr = smem_u32(Ks + st * TILE);
 #pragma unroll
                 for (int kk = 0; kk < D / 16; ++kk) {
                     const uint32_t off = (kk >> 2) * (FA_BM * 128) + (kk & 3) * 32;
-                    umma_bf16(tmem_s, make_desc_sw128(q_addr + off, 0, 1024), make_desc_sw128(k_addr + off, 0, 1024), idesc_qk,
+                    umma_bf16(tmem_base + X * 128, make_desc_sw128(q_addr + off, 0, 1024), make_desc_sw128(k_addr + off, 0, 1024), idesc_qk,
                               kk > 0 ? 1u : 0u);
                 }
-                umma_commit(s_full);
+                umma_commit(&s_full[X]);
             };
-            mbar_wait(q_full, 0);
-            issue_qk(0);
-            for (int j = 0; j < n_tiles; ++j) {
-                const int st = j % FA_KV_STAGES;
-                mbar_wait(p_ready, j & 1);          // P_j is in smem, S_j and O_{j-1} have been consumed
-                tc_fence_after();
-                const uint32_t v_addr = smem_u32(Vs + st * KV_BYTES);
+            auto issue_pv = [&](int X, int j) {
+                const int st = j % FA_STAGES;
+                const uint32_t v_addr = smem_u32(Vs + st * TILE);
 #pragma unroll
                 for (int kk = 0; kk < FA_BN / 16; ++kk) {
-                    const uint64_t da = make_desc_sw128(p_addr + (kk >> 2) * (FA_BM * 128) + (kk & 3) * 32, 0, 1024);
                     // V tile: [128 keys][D] as D/64 blocks of [128 rows][128 B]; MN-major: SBO = 8 k-rows, LBO = next 64-wide d block
                     const uint64_t db = make_desc_sw128(v_addr + kk * 2048, FA_BN * 128, 1024);
-                    umma_bf16(tmem_o, da, db, idesc_pv, kk > 0 ? 1u : 0u);
+                    umma_bf16_ts(tmem_base + 256 + X * 128, tmem_base + X * 128 + kk * 8, db, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
                 }
-                umma_commit(o_full);
-                umma_commit(&kv_empty[st]);         // K_j / V_j (and P_j) free once everything issued so far has completed
-                if (j + 1 < n_tiles) issue_qk(j + 1);
+                umma_commit(&o_done[X]);
+            };
+            mbar_wait(q_full, 0);
+            mbar_wait(&k_full[0], 0);
+            tc_fence_after();
+            if (n_x[0] > 0) issue_qk(0, 0);
+            if (n_x[1] > 0) issue_qk(1, 0);
+            umma_commit(&k_empty[0]);     // K_0 is released once both S_X(0) are complete (commit tracks every MMA issued so far)
+            for (int j = 0; j < n_max; ++j) {
+                const int st = j % FA_STAGES;
+                const uint32_t ph = (j / FA_STAGES) & 1;
+                const int stn = (j + 1) % FA_STAGES;
+                const uint32_t phn = ((j + 1) / FA_STAGES) & 1;
+                mbar_wait(&v_full[st], ph);
+                bool k_next_ready = false;
+#pragma unroll
+                for (int X = 0; X < 2; ++X) {
+                    if (j < n_x[X]) {
+                        mbar_wait(&p_ready[X], j & 1);      // P_X(j) is in TMEM, S_X(j) consumed, O_X rescaled if it had to be
+                        tc_fence_after();
+                        issue_pv(X, j);
+                    }
+                    if (j + 1 < n_x[X]) {
+                        if (!k_next_ready) { mbar_wait(&k_full[stn], phn); tc_fence_after(); k_next_ready = true; }
+                        issue_qk(X, j + 1);
+                    }
+                }
+                umma_commit(&v_empty[st]);                  // V_j free once both PV(j) are done
+                if (k_next_ready) umma_commit(&k_empty[stn]);   // K_{j+1} free once both QK(j+1) are done
             }
         }
+    }
     } else {
-        // ---------------- softmax + output (thread = query row = TMEM lane)
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;" ::: "memory");
+        // ---------------- softmax + output: thread = query row = TMEM lane
+        const int X = (warp - 4) >> 2;
         const int qw = warp & 3;
         const int r = qw * 32 + lane;
-        const int qi = q0 + r;
+        const int qi = q0 + X * FA_BM + r;
         const uint32_t lane_sel = uint32_t(qw * 32) << 16;
-        float o_acc[D];
-#pragma unroll
-        for (int i = 0; i < D; ++i) o_acc[i] = 0.f;
-        float m_run = -INFINITY, l_run = 0.f;
+        const uint32_t tmem_s = tmem_base + X * 128 + lane_sel, tmem_o = tmem_base + 256 + X * 128 + lane_sel;
+        const int nt = n_x[X];
+        float m_used = 0.f, l_run = 0.f;
         const int q_limit = p.causal ? (p.q_pos0 + qi) : 0x7fffffff;   // last visible key for this row
-        for (int j = 0; j < n_tiles; ++j) {
+        const int tile_first_limit = p.causal ? (p.q_pos0 + q0 + X * FA_BM) : 0x7fffffff;   // smallest q_limit of the tile
+        for (int j = 0; j < nt; ++j) {
             const int j0 = j * FA_BN;
-            mbar_wait(s_full, j & 1);
+            mbar_wait(&s_full[X], j & 1);
             tc_fence_after();
+            uint32_t sv[128];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_ld32_raw(tmem_s + c * 32, sv + c * 32);
+            tmem_ld_wait();
+            const bool need_mask = (j0 + FA_BN > sk) || (j0 + FA_BN - 1 > tile_first_limit);   // warp-uniform
+            if (need_mask) {
+#pragma unroll
+                for (int i = 0; i < 128; ++i) {
+                    const int key = j0 + i;
+                    if (!(key < sk && key <= q_limit)) sv[i] = 0xff800000u;   // -inf
+                }
+            }
             float mx = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < FA_BN / 16; ++c) {
-                uint32_t v[32];
-                tmem_ld16(tmem_s + lane_sel + c * 16, v);
-                tmem_ld_wait();
+            for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+            float m_new = mx * p.scale_log2;                 // scale > 0
+            if (m_new == -INFINITY) m_new = (j == 0) ? 0.f : m_used;
+            if (j == 0) {
+                m_used = m_new;
+            } else {
+                // lazy rescale: exponentials stay referenced to m_used until the row maximum has grown by more than 2^8
+                const bool grow = m_new - m_used > 8.0f;
+                if (__any_sync(0xffffffffu, grow)) {
+                    // s_full(j) fired after PV_X(j-1) (same issue thread, in order), so O_X is complete and nobody writes it now
+                    const float m_next = fmaxf(m_used, m_new);
+                    const float f = exp2f(m_used - m_next);
+                    m_used = m_next;
+                    l_run *= f;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int key = j0 + c * 16 + i;
-                    const float x = (key < sk && key <= q_limit) ? __uint_as_float(v[i]) * p.scale_log2 : -INFINITY;
-                    mx = fmaxf(mx, x);
+                    for (int c = 0; c < D / 32; ++c) {
+                        uint32_t ov[32];
+                        tmem_ld32_raw(tmem_o + c * 32, ov);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * f);
+                        tmem_st32(tmem_o + c * 32, ov);
+                    }
                 }
             }
-            const float m_new = fmaxf(m_run, mx);
-            const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
-            const float corr = exp2f(m_run - m_safe);
-            m_run = m_new;
+            const float neg_m = -m_used;
             float rowsum = 0.f;
 #pragma unroll
-            for (int c = 0; c < FA_BN / 16; ++c) {
-                uint32_t v[32];
-                tmem_ld16(tmem_s + lane_sel + c * 16, v);
-                tmem_ld_wait();
-                uint32_t pk[8];
-#pragma unroll
-                for (int i = 0; i < 16; i += 2) {
-                    const int key = j0 + c * 16 + i;
-                    const float x0 = (key < sk && key <= q_limit) ? __uint_as_float(v[i]) * p.scale_log2 : -INFINITY;
-                    const float x1 = (key + 1 < sk && key + 1 <= q_limit) ? __uint_as_float(v[i + 1]) * p.scale_log2 : -INFINITY;
-                    const float p0 = exp2f(x0 - m_safe), p1 = exp2f(x1 - m_safe);
-                    rowsum += p0 + p1;
-                    pk[i >> 1] = pack_bf16x2(p0, p1);
-                }
-                // 16 keys = 32 bytes = 2 chunks of the 128-byte swizzled row of the 64-key block (c >> 2)
-                uint8_t* prow = Ps + (c >> 2) * (FA_BM * 128) + r * 128;
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    const int chunk = ((c & 3) * 2 + t) ^ (r & 7);
-                    *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
-                }
+            for (int i = 0; i < 128; i += 2) {
+                const float p0 = exp2f(fmaf(__uint_as_float(sv[i]), p.scale_log2, neg_m));
+                const float p1 = exp2f(fmaf(__uint_as_float(sv[i + 1]), p.scale_log2, neg_m));
+                rowsum += p0 + p1;
+                sv[i >> 1] = pack_bf16x2(p0, p1);
             }
-            l_run = l_run * corr + rowsum;
-            fence_proxy_async();        // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            l_run += rowsum;
+            tmem_st32(tmem_s, sv);
+            tmem_st32(tmem_s + 32, sv + 32);
+            tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(p_ready);
-            mbar_wait(o_full, j & 1);
-            tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < D / 16; ++c) {
-                uint32_t v[32];
-                tmem_ld16(tmem_o + lane_sel + c * 16, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) o_acc[c * 16 + i] = o_acc[c * 16 + i] * corr + __uint_as_float(v[i]);
-            }
-            tc_fence_before();
+            if (lane == 0) mbar_arrive(&p_ready[X]);
         }
-        if (qi < p.Sq) {
-            const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-            __nv_bfloat16* dst = p.o + ((long long)b * p.Sq + qi) * p.o_ld + (long long)h * D;
+        // final O / l -> bf16.  The tensor-memory loads are warp-collective: every lane executes them, only the global stores
+        // are guarded (rows past Sq in a partially filled tile).
+        if (nt > 0) {
+            mbar_wait(&o_done[X], (nt - 1) & 1);
+            tc_fence_after();
+        }
+        const float inv = (nt > 0 && l_run > 0.f) ? 1.f / l_run : 0.f;
+        __nv_bfloat16* dst = p.o + ((long long)b * p.Sq + qi) * p.o_ld + (long long)h * D;
 #pragma unroll
-            for (int i = 0; i < D; i += 8)
-                *reinterpret_cast<uint4*>(dst + i) =
-                    make_uint4(pack_bf16x2(o_acc[i] * inv, o_acc[i + 1] * inv), pack_bf16x2(o_acc[i + 2] * inv, o_acc[i + 3] * inv),
-                               pack_bf16x2(o_acc[i + 4] * inv, o_acc[i + 5] * inv), pack_bf16x2(o_acc[i + 6] * inv, o_acc[i + 7] * inv));
+        for (int c = 0; c < D / 32; ++c) {
+            uint32_t ov[32];
+            if (nt > 0) { tmem_ld32_raw(tmem_o + c * 32, ov); tmem_ld_wait(); }
+            else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) ov[i] = 0u;
+            }
+            if (qi < p.Sq) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8)
+                    *reinterpret_cast<uint4*>(dst + c * 32 + i) =
+                        make_uint4(pack_bf16x2(__uint_as_float(ov[i]) * inv, __uint_as_float(ov[i + 1]) * inv),
+                                   pack_bf16x2(__uint_as_float(ov[i + 2]) * inv, __uint_as_float(ov[i + 3]) * inv),
+                                   pack_bf16x2(__uint_as_float(ov[i + 4]) * inv, __uint_as_float(ov[i + 5]) * inv),
+                                   pack_bf16x2(__uint_as_float(ov[i + 6]) * inv, __uint_as_float(ov[i + 7]) * inv));
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<TMEM_COLS>(tmem_base);
+        tmem_dealloc<512>(tmem_base);
     }
 }
 
@@ -270,14 +361,14 @@ static int fa_make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_
 
 template <int D>
 static int launch_fa(const FaParams& p, cudaStream_t st) {
-    constexpr int SMEM = FA_BM * D * 2 + 2 * FA_KV_STAGES * FA_BN * D * 2 + FA_BM * FA_BN * 2 + 1024 + 256;
+    constexpr int SMEM = FaSmem<D>::BYTES;
     static bool set = false;
     if (!set) {
-        if (cudaFuncSetAttribute(attention_tcgen05_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) return GROMA_ERR_CUDA;
+        if (cudaFuncSetAttribute(attention_fa2q_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) return GROMA_ERR_CUDA;
         set = true;
     }
-    dim3 grid((p.Sq + FA_BM - 1) / FA_BM, p.H, p.B);
-    attention_tcgen05_kernel<D><<<grid, FA_THREADS, SMEM, st>>>(p);
+    dim3 grid((p.Sq + 2 * FA_BM - 1) / (2 * FA_BM), p.H, p.B);
+    attention_fa2q_kernel<D><<<grid, FA_THREADS, SMEM, st>>>(p);
     return GROMA_LAUNCH_CHECK();
 }
 

@@ -48,6 +48,7 @@ class GromaEngine:
         # mma.sync kernel (145 vs 189 TFLOP/s on the prefill shape: softmax and MMA phases serialise, one CTA per SM); it
         # stays opt-in until the two-Q-tile ping-pong version lands
         self.use_tc_attention = False
+        self.use_megakernel = os.environ.get("GROMA_DECODE_MEGA", "0") == "1"   # one persistent kernel per decode step (csrc/decode_megakernel.cu)
         self.fused_decode = True     # fused reduce epilogues + PDL in the decode step
         self.fused_rope_attn = os.environ.get("GROMA_FUSED_ROPE_ATTN", "1") == "1"   # qkv reduce + RoPE + KV append inside the attention launch
         self.use_pdl = True
@@ -152,19 +153,36 @@ class GromaEngine:
         n_mid, ro = fw.shape[0], cfg.roi_out
         w["flatten.w"] = self._mat(fw.reshape(n_mid, H, ro * ro).permute(0, 2, 1).reshape(n_mid, ro * ro * H))  # (c,h,w) -> (h,w,c)
         w["flatten.b"] = self._vec(sd[re_ + "roi_align.flatten_linear.bias"])
-        # LLaMA
+        # LLaMA.  The projections live in two arenas so that the persistent decode kernel addresses every weight tile through one
+        # TMA descriptor each (include/groma_b200.h: groma_decode_step_args); the per-layer entries of `w` are row views into them
         w["embed"] = self._mat(sd["llm.model.embed_tokens.weight"])
         w["new_embed"] = self._mat(sd["new_input_embs.weight"])
-        for i in range(cfg.llm_layers):
+        L, I, V = cfg.llm_layers, cfg.llm_inter, cfg.vocab + cfg.num_new_token
+        RW = 4 * T + 2 * I
+        arena = torch.empty((L * RW + V, T), dtype=torch.bfloat16, device=self.dev)
+        down = torch.empty((L * T, I), dtype=torch.bfloat16, device=self.dev)
+        lnw = torch.empty((2 * L + 1, T), dtype=torch.float32, device=self.dev)
+        for i in range(L):
             p, o = f"llm.model.layers.{i}.", f"llm.{i}."
-            w[o + "qkv.w"] = self._mat(_cat(*[sd[p + f"self_attn.{n}_proj.weight"] for n in ("q", "k", "v")]))
-            w[o + "o.w"] = self._mat(sd[p + "self_attn.o_proj.weight"])
+            r0 = i * RW
+            for k, n in enumerate(("q", "k", "v")):
+                arena[r0 + k * T: r0 + (k + 1) * T].copy_(sd[p + f"self_attn.{n}_proj.weight"])
+            arena[r0 + 3 * T: r0 + 4 * T].copy_(sd[p + "self_attn.o_proj.weight"])
             g, u = sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"]
-            w[o + "gu.w"] = self._mat(torch.stack([g, u], 1).reshape(2 * g.shape[0], g.shape[1]))  # rows (gate_j, up_j) interleaved
-            w[o + "down.w"] = self._mat(sd[p + "mlp.down_proj.weight"])
-            w[o + "ln1"], w[o + "ln2"] = self._vec(sd[p + "input_layernorm.weight"]), self._vec(sd[p + "post_attention_layernorm.weight"])
-        w["llm.norm"] = self._vec(sd["llm.model.norm.weight"])
-        w["head.w"] = self._mat(_cat(sd["llm.lm_head.weight"], sd["extra_lm_head.weight"]))
+            arena[r0 + 4 * T: r0 + RW].view(I, 2, T)[:, 0].copy_(g)          # rows (gate_j, up_j) interleaved
+            arena[r0 + 4 * T: r0 + RW].view(I, 2, T)[:, 1].copy_(u)
+            down[i * T: (i + 1) * T].copy_(sd[p + "mlp.down_proj.weight"])
+            lnw[2 * i].copy_(sd[p + "input_layernorm.weight"])
+            lnw[2 * i + 1].copy_(sd[p + "post_attention_layernorm.weight"])
+            w[o + "qkv.w"], w[o + "o.w"], w[o + "gu.w"] = arena[r0: r0 + 3 * T], arena[r0 + 3 * T: r0 + 4 * T], arena[r0 + 4 * T: r0 + RW]
+            w[o + "down.w"] = down[i * T: (i + 1) * T]
+            w[o + "ln1"], w[o + "ln2"] = lnw[2 * i], lnw[2 * i + 1]
+        lnw[2 * L].copy_(sd["llm.model.norm.weight"])
+        arena[L * RW: L * RW + cfg.vocab].copy_(sd["llm.lm_head.weight"])
+        arena[L * RW + cfg.vocab:].copy_(sd["extra_lm_head.weight"])
+        w["llm.norm"] = lnw[2 * L]
+        w["head.w"] = arena[L * RW:]
+        self.llm_arena, self.llm_down, self.llm_ln = arena, down, lnw
 
     def _interp_pos(self, pe: torch.Tensor) -> torch.Tensor:
         """transformers-4.32 Dinov2Embeddings.interpolate_pos_encoding: bicubic with scale_factor (g+0.1)/G.
@@ -531,6 +549,83 @@ class GromaEngine:
         )
         return d
 
+    # ------------------------------------------------------------------------------------------ persistent decode step
+    def mega_supported(self, B: int) -> bool:
+        cfg = self.cfg
+        return (cfg.head_dim == 128 and B <= 16 and cfg.llm_hidden % 128 == 0 and cfg.llm_inter % 64 == 0 and
+                (2 * cfg.llm_inter) % 128 == 0 and cfg.llm_hidden <= 8192)
+
+    def _mega_state(self, B: int):
+        """Scratch + argument block of groma_decode_step_fused for batch B (allocated once per B)."""
+        st = getattr(self, "_mk", None)
+        if st is not None and st["B"] == B:
+            return st
+        cfg = self.cfg
+        L, H, Hd, I, V = cfg.llm_layers, cfg.llm_heads, cfg.llm_hidden, cfg.llm_inter, cfg.vocab + cfg.num_new_token
+        n_flags, ws_tile, part, _ = G.decode_step_layout(L, B, H, Hd, I, V)
+        sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
+        # every CTA needs at least one (row tile, k-block) unit of every projection (contributors of a tile are consecutive CTAs)
+        units = min(3 * Hd // 128 * (Hd // 64), Hd // 128 * (Hd // 64), 2 * I // 128 * (Hd // 64), Hd // 128 * (I // 64), (V + 127) // 128 * (Hd // 64))
+        grid = max(1, min(sms, units, int(os.environ.get("GROMA_MEGA_GRID", "100000"))))
+        s_att = max(1, min(32, -(-4 * grid // (B * H))))
+        f32 = lambda n: torch.empty((n,), dtype=torch.float32, device=self.dev)
+        with torch.inference_mode(False):
+            st = dict(B=B, grid=grid, s_att=s_att,
+                      y2=torch.empty((B, Hd), dtype=torch.bfloat16, device=self.dev),
+                      ws_qkv=f32(3 * Hd // 128 * ws_tile), ws_o=f32(Hd // 128 * ws_tile), ws_gu=f32(2 * I // 128 * ws_tile),
+                      ws_down=f32(Hd // 128 * ws_tile), ws_head=f32((V + 127) // 128 * ws_tile),
+                      att_part=f32(B * H * s_att * part), cand_val=f32((V + 127) // 128 * 16),
+                      cand_idx=torch.empty(((V + 127) // 128 * 16,), dtype=torch.int32, device=self.dev),
+                      flags=torch.zeros((n_flags,), dtype=torch.int32, device=self.dev),
+                      status=torch.zeros((8 + 16 * sms,), dtype=torch.int32, device=self.dev), timeline=None)
+        self._mk = st
+        return st
+
+    def decode_step_mega(self, B: int) -> torch.Tensor:
+        """The same greedy step as decode_step() in ONE persistent kernel (csrc/decode_megakernel.cu): reads d['ids'], *pos,
+        kv_len; appends K/V; writes d['logits'], the next ids, and advances pos / kv_len.  CUDA-graph capturable (the flag
+        reset is a fill on the same stream)."""
+        cfg, w = self.cfg, self.w
+        d = self._decode_buffers(B)
+        st = self._mega_state(B)
+        a = G.DecodeStepArgs()
+        a.L, a.B, a.H, a.Hd, a.I, a.V = cfg.llm_layers, B, cfg.llm_heads, cfg.llm_hidden, cfg.llm_inter, cfg.vocab + cfg.num_new_token
+        a.vocab, a.S_att, a.cap = cfg.vocab, st["s_att"], self.kv_cap
+        a.scale, a.eps = 1.0 / math.sqrt(cfg.head_dim), cfg.rms_eps
+        ptr = lambda t: t.data_ptr()
+        a.w_arena, a.w_down, a.embed, a.new_embed, a.ln_w = ptr(self.llm_arena), ptr(self.llm_down), ptr(w["embed"]), ptr(w["new_embed"]), ptr(self.llm_ln)
+        a.kv, a.rope_cos, a.rope_sin = ptr(self.kv), ptr(self.rope_cos), ptr(self.rope_sin)
+        a.ids, a.pos, a.kv_len = ptr(d["ids"]), ptr(d["pos"]), ptr(d["kv_len"])
+        a.x, a.y_attn, a.y_mlp, a.a, a.gu, a.logits = ptr(d["x"]), ptr(d["y"]), ptr(st["y2"]), ptr(d["a"]), ptr(d["gu"]), ptr(d["logits"])
+        for k in ("ws_qkv", "ws_o", "ws_gu", "ws_down", "ws_head", "att_part", "cand_val", "cand_idx", "flags", "status"):
+            setattr(a, k, ptr(st[k]))
+        a.grid = st["grid"]
+        a.timeline = st["timeline"].data_ptr() if st["timeline"] is not None else None
+        if tuple(self.kv.shape[2:4]) != (B, cfg.llm_heads):
+            raise RuntimeError("KV cache was allocated for a different batch")
+        st["flags"].zero_()
+        G.decode_step_fused(a)
+        return d["logits"]
+
+    def check_decode_status(self):
+        """Raise if a dependency wait of the persistent decode kernel timed out (one device->host read; call outside graphs)."""
+        st = getattr(self, "_mk", None)
+        if st is None:
+            return
+        s = st["status"].cpu().tolist()
+        if s[0] != 0:
+            st["status"].zero_()
+            from collections import Counter
+            roles = ("stream-loader", "mma", "worker", "activation-loader")
+            parked = Counter((roles[r], s[8 + (c * 4 + r) * 4], s[8 + (c * 4 + r) * 4 + 1] if os.environ.get("GROMA_MEGA_DEBUG") else 0)
+                             for c in range(st["grid"]) for r in range(4) if s[8 + (c * 4 + r) * 4] != 0)
+            detail = ""
+            if os.environ.get("GROMA_MEGA_DEBUG"):
+                detail = "\n" + "\n".join(f"cta {c} {roles[r]}: {s[8 + (c * 4 + r) * 4: 12 + (c * 4 + r) * 4]}" for c in range(st["grid"]) for r in range(4)
+                                          if s[8 + (c * 4 + r) * 4] != 0)
+            raise G._lib.GromaError(f"persistent decode kernel aborted: code {s[0]} (cta {s[1]}, role {roles[s[2]]}, thread {s[3]}, info {s[4:7]}); "
+                                    f"parked waits (role, code, info): {sorted(parked.items(), key=lambda kv: -kv[1])[:12]}{detail}")
+
     def _decode_splits(self):
         """Split-K factors of the five decode GEMMs: (weight row-tiles of 128) x split should fill whole waves of the 296
         CTA slots (2 per SM); e.g. gate/up has 172 tiles -> 1 split leaves 42% of the slots idle, 5 splits give 860 items =
@@ -594,6 +689,8 @@ class GromaEngine:
         Every shape-dependent scalar lives on the device, so the step is CUDA-graph capturable.
         Per layer: 4 swap-AB tcgen05 GEMMs (weights prefetched under programmatic dependent launch), 4 fused reduce
         epilogues (RoPE+KV append / residual+RMSNorm / SwiGLU / residual+next RMSNorm) and the cluster decode attention."""
+        if self.use_megakernel and self.mega_supported(B):
+            return self.decode_step_mega(B)
         if not self.fused_decode:
             return self._decode_step_unfused(B)
         cfg, w = self.cfg, self.w

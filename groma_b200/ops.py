@@ -539,6 +539,29 @@ def decode_rope_attention(ws: torch.Tensor, cache_k: torch.Tensor, cache_v: torc
     return out
 
 
+# --------------------------------------------------------------------------------------------- persistent decode step
+class DecodeStepArgs(ctypes.Structure):
+    """`groma_decode_step_args` of include/groma_b200.h, field for field."""
+    _fields_ = ([(n, ctypes.c_int32) for n in ("L", "B", "H", "Hd", "I", "V", "vocab", "S_att")] + [("cap", ctypes.c_int64)] +
+                [("scale", ctypes.c_float), ("eps", ctypes.c_float)] +
+                [(n, ctypes.c_void_p) for n in ("w_arena", "w_down", "embed", "new_embed", "ln_w", "kv", "rope_cos", "rope_sin", "ids", "pos",
+                                                "kv_len", "x", "y_attn", "y_mlp", "a", "gu", "logits", "ws_qkv", "ws_o", "ws_gu", "ws_down",
+                                                "ws_head", "att_part", "cand_val", "cand_idx", "flags", "status")] +
+                [("grid", ctypes.c_int32), ("timeline", ctypes.c_void_p)])
+
+
+def decode_step_layout(L: int, B: int, H: int, Hd: int, I: int, V: int):
+    """(number of int32 flags, fp32 scratch floats per 128-row weight tile, floats per attention partial, max rows)."""
+    out = (ctypes.c_int64 * 4)()
+    _lib.check(_L().groma_decode_step_layout(L, B, H, Hd, I, V, ctypes.cast(out, ctypes.c_void_p), None), "groma_decode_step_layout")
+    return [int(v) for v in out]
+
+
+def decode_step_fused(args: DecodeStepArgs) -> None:
+    """One persistent-kernel decode step (all layers + heads + argmax); `flags` must have been zeroed on the same stream."""
+    _chk(_L().groma_decode_step_fused(ctypes.cast(ctypes.pointer(args), ctypes.c_void_p), _stream()), "groma_decode_step_fused")
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # image preprocessing (SURVEY §8f N3)
 PREPROCESS_KMAX = 64

@@ -176,7 +176,9 @@ class Oracle:
         samp = self.r(O.msda_module_core_ref(value, proj, ref, [hw], nH, P))
         return samp
 
-    def proposer(self, hs: List[torch.Tensor]):
+    def proposer(self, hs: List[torch.Tensor], topk_override: Optional[torch.Tensor] = None):
+        """topk_override (tests only): continue with another run's two-stage query selection so that two precisions of the
+        oracle can be compared query by query (the selection itself is tie-sensitive)."""
         cfg, r = self.cfg, self.r
         dt = "perceiver.ddetr_transformer."
         g, D = cfg.grid, cfg.d_model
@@ -218,6 +220,8 @@ class Oracle:
         delta = self.lin(t, f"{dt}bbox_embed.{nb}.layers.2", out_round=False)      # fp32 [B,S,4]
         coord_logits = delta + prop_logit[None]
         topk = torch.stack([torch.from_numpy(np.argsort(-cls[b].numpy(), kind="stable")[:cfg.num_queries].copy()) for b in range(B)])
+        if topk_override is not None:
+            topk = topk_override
         tk = torch.gather(coord_logits, 1, topk[..., None].expand(-1, -1, 4))
         ref = tk.sigmoid()
         npf = D // 2
@@ -494,13 +498,13 @@ class Oracle:
         return h @ w.t()   # fp32
 
     # ------------------------------------------------------------------ GromaModel.forward, prefill branch (groma.py:217-402)
-    def forward_prefill(self, input_ids, images, refer_boxes=None, ground_boxes=None, selected_override=None, labels=None):
+    def forward_prefill(self, input_ids, images, refer_boxes=None, ground_boxes=None, selected_override=None, labels=None, topk_override=None):
         assert self.tok is not None
         hs = self.vit(images)
         self.stages["vit_last"] = hs[-1]
         self.stages["vit_hs"] = hs[-4:]
         img_tok = self.image_tokens(hs[-1])
-        pred, scores, logits = self.proposer(hs)
+        pred, scores, logits = self.proposer(hs, topk_override)
         if selected_override is not None:
             selected, nms_inds = selected_override, None
         else:

@@ -165,3 +165,46 @@ def test_rope_attention_fusion_is_bit_identical(G, ragged):
     assert torch.equal(k1, k2) and torch.equal(v1, v2)
     assert not torch.equal(k1[:, :, pos], kc0[:, :, pos])          # the row really was appended
     assert torch.equal(a1, a2)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_persistent_decode_kernel_matches_the_multi_kernel_step(graph):
+    """csrc/decode_megakernel.cu (one launch per step) against the 294-launch step on the miniature LLaMA: same tokens (up to a
+    near-tie of the logits), logits / appended K,V rows within fp32-summation-order noise, pos / kv_len advanced identically.
+    The miniature runs it with grid = 8 CTAs, S_att = 8 key segments (three of them empty) and 4 contributors per o-proj tile."""
+    from groma.model.groma import GromaConfig, GromaModel
+    from groma_b200.config import SyntheticTokenizer, tiny_config
+    from groma_b200.synth import make_state_dict
+    cfg = tiny_config(box_score_thres=0.0)
+    tok = SyntheticTokenizer(cfg.vocab)
+    m = GromaModel(GromaConfig.from_path_config(cfg), state_dict=make_state_dict(cfg, seed=0), path_config=cfg)
+    m.init_special_token_id(tok)
+    g = torch.Generator().manual_seed(3)
+    images = torch.randn(2, 3, 448, 448, generator=g)
+    ids = torch.randint(10, cfg.vocab, (2, 16), generator=g)
+    ids[:, 2] = tok.map["<image>"]; ids[:, 9] = tok.map["<region>"]
+    ids[1, 13:] = tok.pad_token_id                                   # ragged row: right-padded prompt
+    boxes = [torch.rand(4, 4, generator=g) * 0.6 + 0.2, torch.rand(6, 4, generator=g) * 0.6 + 0.2]
+    n_new = 7
+    runs = {}
+    for mega in (False, True):
+        m.engine.use_megakernel, m.use_cuda_graph, m._graph = mega, graph, None
+        out = m.generate(ids.clone().cuda(), images=images.cuda(), max_new_tokens=n_new, return_dict_in_generate=True,
+                         _selected_override=boxes, _keep_logits=True)
+        T = m._last["ids"].shape[1]
+        runs[mega] = (out.sequences.cpu(), torch.stack([x.cpu() for x in m._step_logits], 1), m.engine.kv[:, :, :, :, T:T + n_new - 1].float().cpu(),
+                      int(m.engine._decode_buffers(2)["pos"].item()), m.engine._decode_buffers(2)["kv_len"].cpu())
+    assert m.engine._mk["grid"] == 8 and m.engine._mk["s_att"] == 8
+    (seq0, lg0, kv0, pos0, kl0), (seq1, lg1, kv1, pos1, kl1) = runs[False], runs[True]
+    assert pos0 == pos1 and torch.equal(kl0, kl1)
+    e = ((lg0 - lg1).abs().max() / lg0.abs().max()).item()
+    ek = ((kv0 - kv1).abs().max() / kv0.abs().max()).item()
+    print(f"graph={graph}: megakernel vs multi-kernel step logits nrel {e:.2e}, appended K/V nrel {ek:.2e}; tokens {seq1[:, 16:].tolist()}")
+    assert e < 5e-3 and ek < 1e-2
+    new0, new1 = seq0[:, 16:], seq1[:, 16:]
+    for b in range(2):
+        for t in range(n_new):
+            if new0[b, t] != new1[b, t]:
+                top2 = lg0[b, t].topk(2).values
+                assert (top2[0] - top2[1]) < 1e-2 * lg0[b, t].abs().max(), f"row {b} step {t} diverged with a clear margin"
+                break

@@ -71,8 +71,9 @@ def test_proposer_and_selection(setup):
     pc, px, sc, _ = m.engine.proposer(hs_g)
     st = m.engine.stages
     print("ddetr_src nrel", nrel(st["ddetr_src"], o.stages["ddetr_src"]), "memory nrel", nrel(st["memory"], o.stages["memory"]))
-    same_topk = (st["topk"].cpu() == o.stages["topk"]).float().mean().item()
-    print(f"topk identical fraction {same_topk:.3f}; enc_cls max abs diff {(st['enc_cls'].cpu() - o.stages['enc_cls']).abs().max():.2e}")
+    tk_g, tk_o = st["topk"].cpu(), o.stages["topk"]
+    same_topk = sum(len(set(tk_g[b].tolist()) & set(tk_o[b].tolist())) for b in range(tk_g.shape[0])) / tk_g.numel()
+    print(f"topk overlap (as sets) {same_topk:.3f}; enc_cls max abs diff {(st['enc_cls'].cpu() - o.stages['enc_cls']).abs().max():.2e}")
     assert nrel(st["memory"], o.stages["memory"]) < 1.5e-2 and rmsrel(st["memory"], o.stages["memory"]) < 6e-3
     # the GPU's top-k is exactly the stable descending order of ITS objectness scores; boxes / scores are then asserted with
     # the oracle's query selection teacher-forced (the boundary of a 60-of-1024 top-k on random-init scores can sit in a near-tie)

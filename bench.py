@@ -316,63 +316,118 @@ def parity_check(model, cfg, sd_cpu, tok, args):
         return {"error": f"{type(e).__name__}: {e}"}
 
 
-def decode_gemm_roofline(model, B, args, step):
-    """Roofline of the dominant kernel, the swap-AB tcgen05 GEMM streaming the LLaMA weights during decode.
-
-    The decode step runs as a CUDA graph, so the kernel's launch duration is measured the way it executes in the timed
-    region: a graph holding exactly the 129 GEMM launches of one decode step (same weights, order, split-K factors and
-    programmatic-dependent-launch attributes, epilogue kernels left out) is replayed between two CUDA events on the
-    launching stream; achieved = algorithmic bytes of those launches / elapsed."""
-    eng = model.engine
-    cfg = eng.cfg
-    from groma_b200 import ops as G
-    d = eng._decode_buffers(B)
-    sp = eng._decode_splits()
-    names = []
-    for i in range(cfg.llm_layers):
-        names += [(f"llm.{i}.qkv.w", sp["qkv"], "y"), (f"llm.{i}.o.w", sp["o"], "q"), (f"llm.{i}.gu.w", sp["gu"], "y"), (f"llm.{i}.down.w", sp["down"], "gu")]
-    names.append(("head.w", sp["head"], "y"))
-    nbytes = 0
-
-    def body():
-        nonlocal nbytes
-        nbytes = 0
-        for wname, split, src in names:
-            W = eng.w[wname]
-            x = d[src]
-            ws = d["ws"][: split * W.shape[0] * B].view(split, B, W.shape[0])
-            G.gemm_swap_ab(x, W, ws, split_k=split, pdl=eng.use_pdl, transposed=True)
-            nbytes += W.numel() * 2 + x.numel() * 2 + ws.numel() * 4
-
+def _graph_of(fn):
     g = torch.cuda.CUDAGraph()
     st = torch.cuda.Stream()
     st.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(st):
-        body()
+        fn()
         with torch.cuda.graph(g, stream=st, capture_error_mode="thread_local"):
-            body()
+            fn()
     torch.cuda.current_stream().wait_stream(st)
+    return g
+
+
+def _time_graph(g, reps=10, before=None):
     for _ in range(3):
+        if before:
+            before()
         g.replay()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 10
-    e0.record()
+    ms = 0.0
     for _ in range(reps):
+        if before:
+            before()
+        e0.record()
         g.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
+        e1.record()
+        torch.cuda.synchronize()
+        ms += e0.elapsed_time(e1)
+    return ms / reps
+
+
+def _traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this round
+    (profiles/r02_dram_traffic.json, written by tools/ncu_summary.py), or None when the kernel was not captured."""
+    path = os.path.join(ROOT, "profiles", "r02_dram_traffic.json")
+    if not os.path.exists(path):
+        return None
+    return json.load(open(path)).get(kernel_key)
+
+
+def decode_gemm_roofline(model, B, args, step):
+    """Roofline of the dominant kernel of the step, measured live with CUDA events on the launching stream.
+
+    Decode is ~2/3 of the step and HBM-bound.  Algorithmic bytes are SURVEY.md section 8(d)'s: the bf16 weights every decode step
+    has to read (13.22 GB: 32 layers x (qkv, o, gate/up, down) + both heads) and, for kernels that also stream the cache, the K/V
+    rows (B x ctx x 0.5 MiB) -- activations, split-K partials and flags are implementation traffic and are NOT counted.
+      * persistent kernel (default when supported): ONE launch per step = `decode_step_megakernel`; its duration is a graph replay
+        of (flag reset + kernel) at the benchmark's mid-decode context.
+      * multi-kernel step: the swap-AB tcgen05 GEMM (129 launches per step, weights only) in a GEMM-only graph with the step's
+        split-K factors and PDL attributes, plus `decode_attention_tma_kernel` (32 launches, K/V only) as the second entry."""
+    eng = model.engine
+    cfg = eng.cfg
+    from groma_b200 import ops as G
+    d = eng._decode_buffers(B)
     peak, how = peaks()
-    ach = nbytes / (ms / 1000.0) / 1e9
-    return {"kernel": "gemm_bf16_tcgen05_kernel<16> (swap-AB weight-streaming GEMM of the decode step; 129 launches per step)",
-            "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": 188094464, "traffic_note": "dram read+write of the gate/up launch (split_k 5) from ncu --set full "
-                                                  "(profiles/r01_decode_gemm_swapab_gateup_v2.md): 180.60 MB + 7.50 MB for 180.4 MB of weights + "
-                                                  "7.0 MB of fp32 partials; not captured for the other four shapes",
-            "peak_source": how, "launches_timed": len(names) * reps, "avg_launch_us": ms * 1000.0 / len(names),
-            "algorithmic_bytes_per_launch": nbytes / len(names),
-            "read_only_ceiling_note": "the 6.58 TB/s peak is a copy (read+write); a read-only stream reaches 7.35 TB/s on this part "
-                                      "(tools/cu/read_bw.cu, LDG.128 or 1-D bulk TMA), so frac vs read-only would be achieved/7350"}
+    Hd, I, V, L = cfg.llm_hidden, cfg.llm_inter, cfg.vocab + cfg.num_new_token, cfg.llm_layers
+    wbytes = L * (4 * Hd * Hd + 3 * Hd * I) * 2 + V * Hd * 2
+    ctx = int(eng.past) - args.new // 2 if getattr(eng, "past", None) else 1030        # mid-decode context of the timed steps
+    ctx = max(ctx, 1)
+    kvbytes = L * 2 * B * (ctx + 1) * Hd * 2
+    note = ("the 6.58 TB/s peak is a copy (read+write); a read-only stream reaches 7.35 TB/s on this part (tools/cu/read_bw.cu, LDG.128 or "
+            "1-D bulk TMA), so frac vs read-only would be achieved/7350")
+
+    def reset():
+        d["pos"].fill_(ctx)
+        d["kv_len"].fill_(ctx + 1)
+
+    entries = []
+    if eng.use_megakernel and eng.mega_supported(B):
+        reset()
+        ms = _time_graph(_graph_of(lambda: eng.decode_step_mega(B)), reps=20, before=reset)
+        eng.check_decode_status()
+        ach = (wbytes + kvbytes) / (ms / 1000.0) / 1e9
+        entries.append({"kernel": "decode_step_megakernel (one persistent launch per decode step: 32 layers + heads + argmax)", "bound": "hbm",
+                        "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": _traffic("decode_step_megakernel"),
+                        "peak_source": how, "launches_timed": 20, "avg_launch_us": ms * 1000.0,
+                        "algorithmic_bytes_per_launch": wbytes + kvbytes, "algorithmic_bytes": {"weights": wbytes, "kv_cache": kvbytes, "ctx": ctx},
+                        "read_only_ceiling_note": note})
+    sp = eng._decode_splits()
+    names = []
+    for i in range(L):
+        names += [(f"llm.{i}.qkv.w", sp["qkv"], "y"), (f"llm.{i}.o.w", sp["o"], "q"), (f"llm.{i}.gu.w", sp["gu"], "y"), (f"llm.{i}.down.w", sp["down"], "gu")]
+    names.append(("head.w", sp["head"], "y"))
+
+    def gemms():
+        for wname, split, src in names:
+            W = eng.w[wname]
+            ws = d["ws"][: split * W.shape[0] * B].view(split, B, W.shape[0])
+            G.gemm_swap_ab(d[src], W, ws, split_k=split, pdl=eng.use_pdl, transposed=True)
+
+    ms = _time_graph(_graph_of(gemms))
+    ach = wbytes / (ms / 1000.0) / 1e9
+    entries.append({"kernel": "gemm_bf16_tcgen05_kernel<16> (swap-AB weight-streaming GEMM of the multi-kernel decode step; 129 launches per step)",
+                    "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": _traffic("gemm_bf16_tcgen05_kernel<16>"), "peak_source": how, "launches_timed": len(names) * 10,
+                    "avg_launch_us": ms * 1000.0 / len(names), "algorithmic_bytes_per_launch": wbytes / len(names),
+                    "algorithmic_bytes": {"weights": wbytes}, "read_only_ceiling_note": note})
+    if cfg.head_dim == 128:
+        import math
+        reset()
+
+        def attns():
+            for i in range(L):
+                G.decode_attention(d["q"], eng.kv[i, 0], eng.kv[i, 1], d["kv_len"], 1.0 / math.sqrt(128), d["a"], pdl=eng.use_pdl)
+        ms = _time_graph(_graph_of(attns))
+        ach = kvbytes / (ms / 1000.0) / 1e9
+        entries.append({"kernel": "decode_attention_tma_kernel<128> (single-query attention over the KV cache; 32 launches per step)", "bound": "hbm",
+                        "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": _traffic("decode_attention_tma_kernel"),
+                        "peak_source": how, "launches_timed": L * 10, "avg_launch_us": ms * 1000.0 / L, "algorithmic_bytes_per_launch": kvbytes / L,
+                        "algorithmic_bytes": {"kv_cache": kvbytes, "ctx": ctx}})
+    primary = dict(entries[0])
+    primary["other_kernels"] = entries[1:]
+    return primary
 
 
 if __name__ == "__main__":

@@ -80,6 +80,12 @@ __device__ __forceinline__ void tmem_ld32_raw(uint32_t taddr, uint32_t* v) {
         : "memory");
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <int D>
 struct FaSmem {
     static constexpr int DBLK = D / 64;                 // 64-column (128-byte) blocks per row of Q/K/V
@@ -255,9 +261,14 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa2q_kernel(const __g
                     if (!(key < sk && key <= q_limit)) sv[i] = 0xff800000u;   // -inf
                 }
             }
-            float mx = -INFINITY;
+            // four independent chains each: a 128-long dependent max / add chain is 500+ cycles of pure latency per tile
+            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-            for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+            for (int i = 0; i < 128; i += 4) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) mx4[t] = fmaxf(mx4[t], __uint_as_float(sv[i + t]));
+            }
+            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
             float m_new = mx * p.scale_log2;                 // scale > 0
             if (m_new == -INFINITY) m_new = (j == 0) ? 0.f : m_used;
             if (j == 0) {
@@ -268,7 +279,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa2q_kernel(const __g
                 if (__any_sync(0xffffffffu, grow)) {
                     // s_full(j) fired after PV_X(j-1) (same issue thread, in order), so O_X is complete and nobody writes it now
                     const float m_next = fmaxf(m_used, m_new);
-                    const float f = exp2f(m_used - m_next);
+                    const float f = ex2_approx(m_used - m_next);
                     m_used = m_next;
                     l_run *= f;
 #pragma unroll
@@ -283,15 +294,18 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa2q_kernel(const __g
                 }
             }
             const float neg_m = -m_used;
-            float rowsum = 0.f;
+            float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int i = 0; i < 128; i += 2) {
-                const float p0 = exp2f(fmaf(__uint_as_float(sv[i]), p.scale_log2, neg_m));
-                const float p1 = exp2f(fmaf(__uint_as_float(sv[i + 1]), p.scale_log2, neg_m));
-                rowsum += p0 + p1;
-                sv[i >> 1] = pack_bf16x2(p0, p1);
+            for (int i = 0; i < 128; i += 8) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i + 2 * t]), p.scale_log2, neg_m));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i + 2 * t + 1]), p.scale_log2, neg_m));
+                    rs4[t] += p0 + p1;
+                    sv[(i >> 1) + t] = pack_bf16x2(p0, p1);
+                }
             }
-            l_run += rowsum;
+            l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
             tmem_st32(tmem_s, sv);
             tmem_st32(tmem_s + 32, sv + 32);
             tmem_st_wait();

@@ -33,14 +33,14 @@
 
 namespace gb {
 
-constexpr int MK_STAGES = 11;
+constexpr int MK_STAGES = 12;
 constexpr int MK_A_BYTES = 16384;   // 128 x 64 bf16 weight tile | 64 keys x 128 dims of K or of V
 constexpr int MK_B_BYTES = 2048;    // 16 tokens x 64 k bf16
 constexpr int MK_STAGE_BYTES = MK_A_BYTES + MK_B_BYTES;
 constexpr int MK_TOK = 16;          // MMA N = max rows per step
 constexpr int MK_WORKERS = 8;       // worker warps: TMEM epilogues (first 4), attention math, reduces
 constexpr int MK_WTHREADS = MK_WORKERS * 32;
-constexpr int MK_THREADS = 64 + MK_WTHREADS + 32;   // warp 0 activation loader, warp 1 MMA issuer, warps 2-9 workers, warp 10 stream loader
+constexpr int MK_THREADS = 64 + MK_WTHREADS + 64;   // warp 0 activation loader, 1 MMA issuer, 2-9 workers, 10 stream loader, 11 L2 prefetcher
 constexpr int MK_TL = 32;           // timeline events per (CTA, role) when MkParams::timeline is set
 constexpr int MK_ACC = 4;           // TMEM accumulator buffers of 16 columns
 constexpr int MK_MAXC = 8;          // contributors per weight-row tile (checked on the host)
@@ -57,6 +57,7 @@ struct MkParams {
     CUtensorMap map_a;      // [B, Hd]: attention output, input of o
     CUtensorMap map_gu;     // [B, I]: SwiGLU output, input of down
     int L, B, H, Hd, I, V, vocab, S_att;
+    int pf_slots;                 // how many 16 KB slots the L2 prefetcher runs ahead of the stream loader (0 = off)
     long long cap;
     float scale_log2, eps;
     const __nv_bfloat16* embed;
@@ -129,6 +130,12 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_expect_tx_only(uint64_t* bar, uint32_t bytes) {   // tx-count += bytes, no arrival
     asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* d, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(d)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_1d(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 1, %0;" ::"n"(MK_WTHREADS) : "memory"); }
 __device__ __forceinline__ void bar_epilogue() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
@@ -162,8 +169,8 @@ __device__ __noinline__ void mk_fail(const MkCtx& c, int code, long long a, long
 __device__ __forceinline__ bool mk_aborted(const MkCtx& c) { return *c.abort_s != 0; }
 // returns false when the wait was abandoned
 __device__ __forceinline__ bool mk_wait_mbar(const MkCtx& c, uint64_t* bar, uint32_t parity, int code, long long info) {
-    if (mk_aborted(c)) return false;
     if (mbar_test(bar, parity)) return true;
+    if (mk_aborted(c)) return false;
     const unsigned long long t0 = mk_now();
     int spins = 0;
     while (!mbar_test(bar, parity)) {
@@ -175,8 +182,8 @@ __device__ __forceinline__ bool mk_wait_mbar(const MkCtx& c, uint64_t* bar, uint
     return true;
 }
 __device__ __forceinline__ bool mk_wait_flag(const MkCtx& c, const int* flag, int need, int code, long long info) {
-    if (mk_aborted(c)) return false;
     if (ld_acquire(flag) >= need) return true;
+    if (mk_aborted(c)) return false;
     const unsigned long long t0 = mk_now();
     int spins = 0;
     while (ld_acquire(flag) < need) {
@@ -219,18 +226,23 @@ __device__ __forceinline__ void mk_contrib(int tile, int kb, int tiles, int G, i
     n = mk_owner((long long)(tile + 1) * kb - 1, U, G) - first + 1;
 }
 
-// key range of attention item i = (b*H + h)*S + seg
+__device__ __forceinline__ int g_tiles_gu(const MkDims& d) { return d.tg; }
+
+// key range of attention item i = seg * (B*H) + (b*H + h): segment-major, so the round-robin i -> CTA mixes long and short
+// segments on every CTA; the 64-key chunks of a row are dealt to its S segments as evenly as possible
 struct MkItem { int b, h, seg, k_begin, n, nch; };
 __device__ __forceinline__ MkItem mk_item(const MkParams& p, const int* kvlen_s, int i) {
     MkItem it;
-    const int bh = i / p.S_att;
-    it.seg = i - bh * p.S_att;
+    const int BH = p.B * p.H;
+    it.seg = i / BH;
+    const int bh = i - it.seg * BH;
     it.b = bh / p.H; it.h = bh - it.b * p.H;
     const int n_all = kvlen_s[it.b];
-    const int per = (((n_all + p.S_att - 1) / p.S_att + MK_KEYS - 1) / MK_KEYS) * MK_KEYS;
-    it.k_begin = min(it.seg * per, n_all);
-    it.n = min(per, n_all - it.k_begin);
-    it.nch = (it.n + MK_KEYS - 1) / MK_KEYS;
+    const int C = (n_all + MK_KEYS - 1) / MK_KEYS;
+    const int c0 = it.seg * C / p.S_att, c1 = (it.seg + 1) * C / p.S_att;
+    it.k_begin = min(c0 * MK_KEYS, n_all);
+    it.n = min(c1 * MK_KEYS, n_all) - it.k_begin;
+    it.nch = c1 - c0;
     return it;
 }
 __device__ __forceinline__ int mk_kv_slots(const MkParams& p, const int* kvlen_s) {
@@ -239,82 +251,6 @@ __device__ __forceinline__ int mk_kv_slots(const MkParams& p, const int* kvlen_s
     for (int i = blockIdx.x; i < NI; i += gridDim.x) n += 2 * mk_item(p, kvlen_s, i).nch;
     return n;
 }
-
-// One entry of the producer's slot list.
-struct MkSlot {
-    int kind;                   // 0 = GEMM unit, 1 = K or V chunk
-    const CUtensorMap* amap; int a_c0, a_c1;
-    const CUtensorMap* bmap; int b_c0;
-    const int* flag; int need;  // dependency of the B part
-    const void* src; uint32_t bytes;
-};
-struct MkSlotIter {
-    const MkParams* p; const MkDims* d; const int* kvlen_s;
-    int layer, phase;           // phase: 0 qkv, 1 attention, 2 o, 3 gate/up, 4 down ; layer == L: head only
-    MkGemm g; int u;
-    int item, ch, which;        // attention cursor: item index, chunk, 0 = K / 1 = V
-    MkItem it;
-    bool in_phase;
-    __device__ void init(const MkParams* p_, const MkDims* d_, const int* kv_) {
-        p = p_; d = d_; kvlen_s = kv_; layer = 0; phase = 0; in_phase = false;
-    }
-    __device__ void enter() {
-        in_phase = true;
-        if (phase == 1) {
-            item = blockIdx.x; ch = 0; which = 0;
-            const int NI = p->B * p->H * p->S_att;
-            while (item < NI) { it = mk_item(*p, kvlen_s, item); if (it.nch > 0) break; item += gridDim.x; }
-        } else {
-            g = mk_gemm(*p, *d, layer, layer == p->L ? 4 : (phase == 0 ? 0 : phase - 1));
-            u = g.u0;
-        }
-    }
-    __device__ bool next(MkSlot& s) {
-        for (;;) {
-            if (layer > p->L) return false;
-            if (!in_phase) enter();
-            if (phase == 1) {
-                const int NI = p->B * p->H * p->S_att;
-                if (item < NI) {
-                    s.kind = 1;
-                    const long long bh = (long long)it.b * p->H + it.h;
-                    const __nv_bfloat16* base = p->kv + ((((long long)layer * 2 + which) * p->B * p->H + bh) * p->cap + it.k_begin + (long long)ch * MK_KEYS) * MK_D;
-                    s.src = base;
-                    s.bytes = (uint32_t)min(MK_KEYS, it.n - ch * MK_KEYS) * MK_D * 2;
-                    if (which == 0) which = 1;
-                    else {
-                        which = 0;
-                        if (++ch == it.nch) {
-                            ch = 0; item += gridDim.x;
-                            while (item < NI) { it = mk_item(*p, kvlen_s, item); if (it.nch > 0) break; item += gridDim.x; }
-                        }
-                    }
-                    return true;
-                }
-            } else if (u < g.u1) {
-                const int tile = u / g.kb, kb = u - tile * g.kb;
-                s.kind = 0;
-                s.amap = (g.which == 3) ? &p->map_wd : &p->map_w;
-                s.a_c0 = kb * 64; s.a_c1 = g.row0 + tile * 128;
-                s.b_c0 = kb * 64;
-                int* fl = p->flags + layer * d->lstride;
-                switch (g.which) {
-                    case 0: s.bmap = &p->map_yattn; s.flag = p->flags + d->f_tok + layer * 2; s.need = p->B; break;
-                    case 1: s.bmap = &p->map_a; s.flag = fl + d->f_head + kb / 2; s.need = p->B; break;
-                    case 2: s.bmap = &p->map_ymlp; s.flag = p->flags + d->f_tok + layer * 2 + 1; s.need = p->B; break;
-                    case 3: s.bmap = &p->map_gu; s.flag = fl + d->f_gub + kb; s.need = 1; break;
-                    default: s.bmap = &p->map_yattn; s.flag = p->flags + d->f_tok + p->L * 2; s.need = p->B; break;
-                }
-                ++u;
-                return true;
-            }
-            // phase exhausted
-            in_phase = false;
-            if (layer == p->L) { layer = p->L + 1; return false; }
-            if (++phase == 5) { phase = 0; ++layer; }
-        }
-    }
-};
 
 // ---------------------------------------------------------------------------------------------- kernel
 struct MkSmemTail {
@@ -382,72 +318,154 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_megakernel(const __
     const uint32_t tmem_base = T.tmem_holder[0];
     const int pos = *p.pos;
     const int nkv = mk_kv_slots(p, T.kvlen);      // K/V slots of this CTA per layer
-    MkCtx ctx{&p, &T.abort_flag, warp == 0 ? 3 : (warp == 1 ? 1 : (warp == 10 ? 0 : 2))};
+    MkCtx ctx{&p, &T.abort_flag, warp == 0 ? 3 : (warp == 1 ? 1 : (warp >= 10 ? 0 : 2))};
 
     if (warp == 10) {
-        // =========================================================== stream loader: weights and cached K/V, never waits for data
+        // =========================================================== stream loader: weights and cached K/V, never waits for data.
+        // One lane, a handful of instructions per 16 KB slot (no divisions in the loops): it has to sustain one slot per ~0.3 us.
         if (lane == 0) {
-            MkSlotIter it;
-            it.init(&p, &d, T.kvlen);
-            MkSlot sa;
-            int seqA = 0;
+            int seq = 0;
+            bool ok = true;
             mk_tl(ctx, 0);
-            while (it.next(sa)) {
-                const int s = seqA % MK_STAGES;
-                if (!mk_wait_mbar(ctx, &T.empty_bar[s], (uint32_t)(((seqA / MK_STAGES) & 1) ^ 1), 101, seqA)) break;
-                uint8_t* dst = smem + s * MK_STAGE_BYTES;
-                if (sa.kind == 0) {
-                    mbar_expect_tx_only(&T.full_bar[s], MK_A_BYTES);
-                    tma_load_2d(dst, sa.amap, &T.full_bar[s], sa.a_c0, sa.a_c1);
-                } else {
-                    mbar_expect_tx(&T.full_bar[s], sa.bytes);
-                    bulk_load_1d(dst, sa.src, sa.bytes, &T.full_bar[s]);
+            auto slot_ptr = [&](int sq) -> uint8_t* { return smem + (sq % MK_STAGES) * MK_STAGE_BYTES; };
+            for (int layer = 0; layer <= p.L && ok; ++layer) {
+                for (int ph = 0; ph < 5 && ok; ++ph) {
+                    if (layer == p.L && ph > 0) break;
+                    if (ph == 1) {
+                        const int NI = p.B * p.H * p.S_att;
+                        const long long plane = (long long)p.B * p.H * p.cap * MK_D;       // elements of one layer's K (or V)
+                        const __nv_bfloat16* kl = p.kv + (long long)layer * 2 * plane;
+                        for (int i = cta; i < NI && ok; i += G) {
+                            const MkItem it = mk_item(p, T.kvlen, i);
+                            const __nv_bfloat16* kb = kl + (((long long)it.b * p.H + it.h) * p.cap + it.k_begin) * MK_D;
+                            int left = it.n;
+                            for (int ch = 0; ch < it.nch; ++ch, left -= MK_KEYS, kb += MK_KEYS * MK_D) {
+                                const uint32_t bytes = (uint32_t)min(MK_KEYS, left) * MK_D * 2;
+#pragma unroll
+                                for (int kv = 0; kv < 2; ++kv) {
+                                    const int s = seq % MK_STAGES;
+                                    if (!mk_wait_mbar(ctx, &T.empty_bar[s], (uint32_t)(((seq / MK_STAGES) & 1) ^ 1), 101, seq)) { ok = false; break; }
+                                    mbar_expect_tx(&T.full_bar[s], bytes);
+                                    bulk_load_1d(slot_ptr(seq), kv ? kb + plane : kb, bytes, &T.full_bar[s]);
+                                    T.seq_a = ++seq;
+                                }
+                                if (!ok) break;
+                            }
+                        }
+                        continue;
+                    }
+                    const MkGemm g = mk_gemm(p, d, layer, layer == p.L ? 4 : (ph == 0 ? 0 : ph - 1));
+                    const CUtensorMap* amap = (g.which == 3) ? &p.map_wd : &p.map_w;
+                    int tile = g.u0 / g.kb, k = g.u0 - tile * g.kb;
+                    for (int u = g.u0; u < g.u1; ++u) {
+                        const int s = seq % MK_STAGES;
+                        if (!mk_wait_mbar(ctx, &T.empty_bar[s], (uint32_t)(((seq / MK_STAGES) & 1) ^ 1), 101, seq)) { ok = false; break; }
+                        mbar_expect_tx_only(&T.full_bar[s], MK_A_BYTES);
+                        tma_load_2d(slot_ptr(seq), amap, &T.full_bar[s], k * 64, g.row0 + tile * 128);
+                        T.seq_a = ++seq;       // after the expect_tx above: the activation loader may now arrive on this slot's barrier
+                        if (++k == g.kb) { k = 0; ++tile; }
+                    }
                 }
-                T.seq_a = ++seqA;          // after the expect_tx above: the activation loader may now arrive on this slot's barrier
             }
             mk_tl(ctx, 1);
         }
-    } else if (warp == 0) {
-        // =========================================================== activation loader: the 2 KB B operand of every GEMM slot, as soon
-        // as its producer has published it
-        if (lane == 0) {
-            MkSlotIter it;
-            it.init(&p, &d, T.kvlen);
-            MkSlot sb;
-            int seqB = 0;
-            const int* ok_flag = nullptr; int ok_need = 0;
-            bool okb = true;
-            while (okb && it.next(sb)) {
-                if (sb.kind == 0) {
-                    if (!(sb.flag == ok_flag && sb.need == ok_need)) {
-                        okb = mk_wait_flag(ctx, sb.flag, sb.need, 102, seqB);
-                        if (!okb) break;
-                        ok_flag = sb.flag; ok_need = sb.need;
-                        fence_proxy_async_all();
-                    }
-                    if (T.seq_a <= seqB) {      // the slot's weight load (and its expect_tx) must have been issued first
-                        const unsigned long long t0 = mk_now();
-                        int spins = 0;
-                        while (T.seq_a <= seqB) {
-                            if ((++spins & 255) == 0) {
-                                if (mk_aborted(ctx) || ld_relaxed(p.status) != 0) { mk_note(ctx, 103, seqB, T.seq_a); T.abort_flag = 1; okb = false; break; }
-                                if (mk_now() - t0 > MK_TIMEOUT_NS) { mk_fail(ctx, 103, seqB, T.seq_a); okb = false; break; }
+    } else if (warp == 11) {
+        // =========================================================== L2 prefetcher: the same slot list as the stream loader, pf_slots
+        // ahead of it.  HBM latency under load (~3 us) x 7 TB/s is more than the 200 KB a ring can keep in flight per SM; with the
+        // tiles already in L2 the ring only has to cover L2 latency.
+        if (lane == 0 && p.pf_slots > 0) {
+            int seq = 0;
+            bool ok = true;
+            auto throttle = [&]() {
+                if (seq - T.seq_a < p.pf_slots) return;
+                int spins = 0;
+                while (seq - T.seq_a >= p.pf_slots) {
+                    if ((++spins & 1023) == 0 && (mk_aborted(ctx) || ld_relaxed(p.status) != 0)) { ok = false; return; }
+                }
+            };
+            for (int layer = 0; layer <= p.L && ok; ++layer) {
+                for (int ph = 0; ph < 5 && ok; ++ph) {
+                    if (layer == p.L && ph > 0) break;
+                    if (ph == 1) {
+                        const int NI = p.B * p.H * p.S_att;
+                        const long long plane = (long long)p.B * p.H * p.cap * MK_D;
+                        const __nv_bfloat16* kl = p.kv + (long long)layer * 2 * plane;
+                        for (int i = cta; i < NI && ok; i += G) {
+                            const MkItem it = mk_item(p, T.kvlen, i);
+                            const __nv_bfloat16* kb = kl + (((long long)it.b * p.H + it.h) * p.cap + it.k_begin) * MK_D;
+                            int left = it.n;
+                            for (int ch = 0; ch < it.nch && ok; ++ch, left -= MK_KEYS, kb += MK_KEYS * MK_D) {
+                                const uint32_t bytes = (uint32_t)min(MK_KEYS, left) * MK_D * 2;
+                                throttle();
+                                bulk_prefetch_1d(kb, bytes);
+                                bulk_prefetch_1d(kb + plane, bytes);
+                                seq += 2;
                             }
                         }
-                        if (!okb) break;
+                        continue;
                     }
-                    const int s = seqB % MK_STAGES;
-                    mbar_expect_tx(&T.full_bar[s], MK_B_BYTES);
-                    tma_load_2d(smem + s * MK_STAGE_BYTES + MK_A_BYTES, sb.bmap, &T.full_bar[s], sb.b_c0, 0);
+                    const MkGemm g = mk_gemm(p, d, layer, layer == p.L ? 4 : (ph == 0 ? 0 : ph - 1));
+                    const CUtensorMap* amap = (g.which == 3) ? &p.map_wd : &p.map_w;
+                    int tile = g.u0 / g.kb, k = g.u0 - tile * g.kb;
+                    for (int u = g.u0; u < g.u1 && ok; ++u, ++seq) {
+                        throttle();
+                        tma_prefetch_2d(amap, k * 64, g.row0 + tile * 128);
+                        if (++k == g.kb) { k = 0; ++tile; }
+                    }
                 }
-                ++seqB;
+            }
+        }
+    } else if (warp == 0) {
+        // =========================================================== activation loader: the 2 KB B operand of every GEMM slot, as soon as
+        // the phase that produces it has published it (one counter per dependency, polled once per phase)
+        if (lane == 0) {
+            int seq = 0;
+            bool ok = true;
+            for (int layer = 0; layer <= p.L && ok; ++layer) {
+                int* fl = p.flags + layer * d.lstride;
+                for (int ph = 0; ph < 5 && ok; ++ph) {
+                    if (layer == p.L && ph > 0) break;
+                    if (ph == 1) { seq += nkv; continue; }
+                    const MkGemm g = mk_gemm(p, d, layer, layer == p.L ? 4 : (ph == 0 ? 0 : ph - 1));
+                    const CUtensorMap* bmap; const int* flag; int need;
+                    switch (g.which) {
+                        case 0: bmap = &p.map_yattn; flag = p.flags + d.f_tok + layer * 2; need = p.B; break;
+                        case 1: bmap = &p.map_a; flag = fl + d.f_head; need = p.B * p.H; break;
+                        case 2: bmap = &p.map_ymlp; flag = p.flags + d.f_tok + layer * 2 + 1; need = p.B; break;
+                        case 3: bmap = &p.map_gu; flag = fl + d.f_gub; need = g_tiles_gu(d); break;
+                        default: bmap = &p.map_yattn; flag = p.flags + d.f_tok + p.L * 2; need = p.B; break;
+                    }
+                    if (g.u0 < g.u1) {
+                        ok = mk_wait_flag(ctx, flag, need, 102, seq);
+                        if (!ok) break;
+                        fence_proxy_async_all();
+                    }
+                    int k = g.u0 % g.kb;
+                    for (int u = g.u0; u < g.u1; ++u, ++seq) {
+                        if (T.seq_a <= seq) {      // the slot's weight load (and its expect_tx) must have been issued first
+                            const unsigned long long t0 = mk_now();
+                            int spins = 0;
+                            while (T.seq_a <= seq) {
+                                if ((++spins & 255) == 0) {
+                                    if (mk_aborted(ctx) || ld_relaxed(p.status) != 0) { mk_note(ctx, 103, seq, T.seq_a); T.abort_flag = 1; ok = false; break; }
+                                    if (mk_now() - t0 > MK_TIMEOUT_NS) { mk_fail(ctx, 103, seq, T.seq_a); ok = false; break; }
+                                }
+                            }
+                            if (!ok) break;
+                        }
+                        const int s = seq % MK_STAGES;
+                        mbar_expect_tx(&T.full_bar[s], MK_B_BYTES);
+                        tma_load_2d(smem + s * MK_STAGE_BYTES + MK_A_BYTES, bmap, &T.full_bar[s], k * 64, 0);
+                        if (++k == g.kb) k = 0;
+                    }
+                }
             }
         }
     } else if (warp == 1) {
         // =========================================================== MMA issuer
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_bf16(128, MK_TOK);
-            long long seq = 0;
+            int seq = 0;
             int acc = 0; uint32_t acc_phase = 0;
             bool ok = true;
             for (int layer = 0; layer <= p.L && ok; ++layer) {
@@ -482,7 +500,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_megakernel(const __
                         const uint32_t d_tmem = tmem_base + acc * MK_TOK;
                         const int ustart = u;
                         for (; u < uend; ++u, ++seq) {
-                            const int s = (int)(seq % MK_STAGES);
+                            const int s = seq % MK_STAGES;
                             ok = mk_wait_mbar(ctx, &T.full_bar[s], (uint32_t)((seq / MK_STAGES) & 1), 202, seq);
                             if (!ok) break;
                             tc_fence_after();
@@ -508,7 +526,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_megakernel(const __
         const int grp = lane >> 4, l16 = lane & 15;
         const int hw = w * 2 + grp;             // half-warp id 0..15
         const int q4 = warp & 3;                // TMEM lane quarter of this warp
-        long long seq = 0;
+        int seq = 0;
         int acc = 0; uint32_t acc_phase = 0;
         bool ok = true;
         int* tokdone = p.flags + d.f_tok;
@@ -678,7 +696,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_megakernel(const __
                         float sc[4];
                         // ---- K slot: 4 keys per half-warp (key j = hw + 16*u)
                         {
-                            const int s = (int)(seq % MK_STAGES);
+                            const int s = seq % MK_STAGES;
                             ok = ok && mk_wait_mbar(ctx, &T.full_bar[s], (uint32_t)((seq / MK_STAGES) & 1), 504, seq);
                             const __nv_bfloat16* ks = reinterpret_cast<const __nv_bfloat16*>(smem + s * MK_STAGE_BYTES);
 #pragma unroll
@@ -706,7 +724,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_megakernel(const __
                         }
                         // ---- V slot
                         {
-                            const int s = (int)(seq % MK_STAGES);
+                            const int s = seq % MK_STAGES;
                             ok = ok && mk_wait_mbar(ctx, &T.full_bar[s], (uint32_t)((seq / MK_STAGES) & 1), 505, seq);
                             const __nv_bfloat16* vs = reinterpret_cast<const __nv_bfloat16*>(smem + s * MK_STAGE_BYTES);
                             uint4 vv[4];
@@ -764,7 +782,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_megakernel(const __
                     bool finish = true;          // this CTA writes the final row
                     if (p.S_att > 1) {
                         if (tid < MK_D && ok) {
-                            float* pp = p.att_part + (long long)i * MK_PART;
+                            float* pp = p.att_part + ((long long)bh * p.S_att + it.seg) * MK_PART;
                             if (tid == 0) { pp[0] = M; pp[1] = den; }
                             pp[4 + tid] = num;
                         }
@@ -787,7 +805,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_megakernel(const __
                     }
                     if (finish && ok && tid < MK_D) aout[tid] = __float2bfloat16_rn(den > 0.f ? num / den : 0.f);
                     sync_ok();                   // also protects st_* / s_new reuse by the next item
-                    if (finish && ok && tid == 0) { fence_proxy_async_all(); red_release_add(fl + d.f_head + it.h, 1); }
+                    if (finish && ok && tid == 0) { fence_proxy_async_all(); red_release_add(fl + d.f_head, 1); }
                 }
             }
             if (tid == 0) T.attn_done = layer + 1;      // every worker warp is past the last item's final barrier: the K/V slots are drained
@@ -822,7 +840,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_megakernel(const __
                         make_uint2(pack_bf16x2(silu(a0.x) * a0.y, silu(a0.z) * a0.w), pack_bf16x2(silu(a1.x) * a1.y, silu(a1.z) * a1.w));
                 }
                 sync_ok();
-                if (ok && tid == 0) { fence_proxy_async_all(); red_release_add(fl + d.f_gub + j, 1); }
+                if (ok && tid == 0) { fence_proxy_async_all(); red_release_add(fl + d.f_gub, 1); }
             }
             if (tid == 0 && layer == 0) mk_tl(ctx, 6);
             // ---------------- down projection, residual + the next layer's input RMSNorm (or the final norm)
@@ -978,7 +996,7 @@ GROMA_API int32_t groma_decode_step_fused(const groma_decode_step_args* a, void*
     if ((rc = mk_map(&p.map_ymlp, a->y_mlp, a->B, a->Hd, MK_TOK))) return rc;
     if ((rc = mk_map(&p.map_a, a->a, a->B, a->Hd, MK_TOK))) return rc;
     if ((rc = mk_map(&p.map_gu, a->gu, a->B, a->I, MK_TOK))) return rc;
-    p.L = a->L; p.B = a->B; p.H = a->H; p.Hd = a->Hd; p.I = a->I; p.V = a->V; p.vocab = a->vocab; p.S_att = a->S_att;
+    p.pf_slots = a->l2_prefetch_slots; p.L = a->L; p.B = a->B; p.H = a->H; p.Hd = a->Hd; p.I = a->I; p.V = a->V; p.vocab = a->vocab; p.S_att = a->S_att;
     p.cap = a->cap; p.scale_log2 = a->scale * 1.4426950408889634f; p.eps = a->eps;
     p.embed = reinterpret_cast<const __nv_bfloat16*>(a->embed); p.new_embed = reinterpret_cast<const __nv_bfloat16*>(a->new_embed);
     p.ln_w = a->ln_w; p.kv = reinterpret_cast<__nv_bfloat16*>(a->kv); p.rope_cos = a->rope_cos; p.rope_sin = a->rope_sin;

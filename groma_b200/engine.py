@@ -44,10 +44,10 @@ class GromaEngine:
         self.decode_tiled = os.environ.get("GROMA_DECODE_TILED", "0") == "1"   # decode GEMMs stream a tile-major weight copy (+13 GB)
         self._wt: Dict[str, torch.Tensor] = {}
         self.use_2cta = True           # cta_group::2 GEMM for the large prefill projections and 3x3 convs
-        # tcgen05 flash attention (attention_tcgen05.cu) is parity-green but, in its first single-Q-tile form, slower than the
-        # mma.sync kernel (145 vs 189 TFLOP/s on the prefill shape: softmax and MMA phases serialise, one CTA per SM); it
-        # stays opt-in until the two-Q-tile ping-pong version lands
-        self.use_tc_attention = False
+        # tcgen05 flash attention (attention_tcgen05.cu: two query tiles in ping-pong, P in tensor memory) for head dims 64 / 128
+        # (DINOv2 and the LLaMA prefill); the mma.sync kernel stays for head dim 32 (Deformable-DETR self-attention) and the
+        # miniature test shapes.  GROMA_TC_ATTENTION=0 switches back for A/B runs.
+        self.use_tc_attention = os.environ.get("GROMA_TC_ATTENTION", "1") == "1"
         self.use_megakernel = os.environ.get("GROMA_DECODE_MEGA", "0") == "1"   # one persistent kernel per decode step (csrc/decode_megakernel.cu)
         self.fused_decode = True     # fused reduce epilogues + PDL in the decode step
         self.fused_rope_attn = os.environ.get("GROMA_FUSED_ROPE_ATTN", "1") == "1"   # qkv reduce + RoPE + KV append inside the attention launch
@@ -567,7 +567,7 @@ class GromaEngine:
         # every CTA needs at least one (row tile, k-block) unit of every projection (contributors of a tile are consecutive CTAs)
         units = min(3 * Hd // 128 * (Hd // 64), Hd // 128 * (Hd // 64), 2 * I // 128 * (Hd // 64), Hd // 128 * (I // 64), (V + 127) // 128 * (Hd // 64))
         grid = max(1, min(sms, units, int(os.environ.get("GROMA_MEGA_GRID", "100000"))))
-        s_att = max(1, min(32, -(-4 * grid // (B * H))))
+        s_att = max(1, min(32, -(-int(os.environ.get("GROMA_MEGA_ITEMS_PER_CTA", "4")) * grid // (B * H))))
         f32 = lambda n: torch.empty((n,), dtype=torch.float32, device=self.dev)
         with torch.inference_mode(False):
             st = dict(B=B, grid=grid, s_att=s_att,
@@ -600,6 +600,7 @@ class GromaEngine:
         for k in ("ws_qkv", "ws_o", "ws_gu", "ws_down", "ws_head", "att_part", "cand_val", "cand_idx", "flags", "status"):
             setattr(a, k, ptr(st[k]))
         a.grid = st["grid"]
+        a.l2_prefetch_slots = int(os.environ.get("GROMA_MEGA_PREFETCH", "0"))
         a.timeline = st["timeline"].data_ptr() if st["timeline"] is not None else None
         if tuple(self.kv.shape[2:4]) != (B, cfg.llm_heads):
             raise RuntimeError("KV cache was allocated for a different batch")

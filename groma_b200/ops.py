@@ -547,7 +547,7 @@ class DecodeStepArgs(ctypes.Structure):
                 [(n, ctypes.c_void_p) for n in ("w_arena", "w_down", "embed", "new_embed", "ln_w", "kv", "rope_cos", "rope_sin", "ids", "pos",
                                                 "kv_len", "x", "y_attn", "y_mlp", "a", "gu", "logits", "ws_qkv", "ws_o", "ws_gu", "ws_down",
                                                 "ws_head", "att_part", "cand_val", "cand_idx", "flags", "status")] +
-                [("grid", ctypes.c_int32), ("timeline", ctypes.c_void_p)])
+                [("grid", ctypes.c_int32), ("l2_prefetch_slots", ctypes.c_int32), ("timeline", ctypes.c_void_p)])
 
 
 def decode_step_layout(L: int, B: int, H: int, Hd: int, I: int, V: int):

@@ -241,6 +241,7 @@ typedef struct groma_decode_step_args {
     int32_t* flags;
     int32_t* status;
     int32_t grid;
+    int32_t l2_prefetch_slots; /* 16 KB slots the L2 prefetcher keeps ahead of the shared-memory ring (0 = no prefetch) */
     int64_t* timeline;   /* optional (may be null): int64[grid*4*32] %globaltimer stamps of the phase boundaries, for profiling */
 } groma_decode_step_args;
 int32_t groma_decode_step_fused(const groma_decode_step_args* args /*host*/, void* stream);

@@ -171,7 +171,7 @@ def test_rope_attention_fusion_is_bit_identical(G, ragged):
 def test_persistent_decode_kernel_matches_the_multi_kernel_step(graph):
     """csrc/decode_megakernel.cu (one launch per step) against the 294-launch step on the miniature LLaMA: same tokens (up to a
     near-tie of the logits), logits / appended K,V rows within fp32-summation-order noise, pos / kv_len advanced identically.
-    The miniature runs it with grid = 8 CTAs, S_att = 8 key segments (three of them empty) and 4 contributors per o-proj tile."""
+    The miniature runs it with grid = 8 CTAs, more key segments than key chunks (most are empty) and 4 contributors per o-proj tile."""
     from groma.model.groma import GromaConfig, GromaModel
     from groma_b200.config import SyntheticTokenizer, tiny_config
     from groma_b200.synth import make_state_dict
@@ -194,7 +194,7 @@ def test_persistent_decode_kernel_matches_the_multi_kernel_step(graph):
         T = m._last["ids"].shape[1]
         runs[mega] = (out.sequences.cpu(), torch.stack([x.cpu() for x in m._step_logits], 1), m.engine.kv[:, :, :, :, T:T + n_new - 1].float().cpu(),
                       int(m.engine._decode_buffers(2)["pos"].item()), m.engine._decode_buffers(2)["kv_len"].cpu())
-    assert m.engine._mk["grid"] == 8 and m.engine._mk["s_att"] == 8
+    assert m.engine._mk["grid"] == 8 and m.engine._mk["s_att"] > 5      # more key segments than 64-key chunks: some are empty
     (seq0, lg0, kv0, pos0, kl0), (seq1, lg1, kv1, pos1, kl1) = runs[False], runs[True]
     assert pos0 == pos1 and torch.equal(kl0, kl1)
     e = ((lg0 - lg1).abs().max() / lg0.abs().max()).item()

@@ -109,7 +109,8 @@ class CustomDDETRModel(torch.nn.Module):
         hs = self.engine.vit(images)
         pc, _, _, logits = self.engine.proposer(hs)
         q = self.engine.cfg.num_queries
-        return DetectionOutput(logits=logits, pred_boxes=pc[:, :q])
+        # the engine's proposer returns buffers owned by its CUDA graph: hand out copies, the caller may keep them across calls
+        return DetectionOutput(logits={k: v.clone() for k, v in logits.items()}, pred_boxes=pc[:, :q].clone())
 
 
 try:

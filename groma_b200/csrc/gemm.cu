@@ -61,7 +61,7 @@ static int launch_gemm_2cta(const GemmParams& p, cudaStream_t stream) {
     int clusters = num_sms() / 2;
     if (work < clusters) clusters = work;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(clusters * 2); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
+    cfg.gridDim = dim3(clusters * 2); cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -89,14 +89,14 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
     const int grid = work < slots ? work : slots;
     if (p.flags & GF_PDL) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         return cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, 1>, p) == cudaSuccess ? GROMA_OK : GROMA_ERR_CUDA;
     }
-    gemm_bf16_tcgen05_kernel<BN, 1><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+    gemm_bf16_tcgen05_kernel<BN, 1><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? GROMA_OK : GROMA_ERR_CUDA;
 }
 
@@ -186,6 +186,7 @@ GROMA_API int32_t groma_gemm_bf16(const void* A, int64_t a_rows, int64_t lda, co
             if (bn == 128 && m_tiles * ((N + 127) / 128) * split_k < num_sms() / 2 && N >= 128) bn = 64;
         }
     }
+    if (tile_counters && gemm_epi_warps(bn == 512 ? 256 : bn) != 4) return GROMA_ERR_UNSUPPORTED;   // fused split-K finish: narrow (decode) tiles only
     GemmParams p;
     int rc = make_tma_2d(&p.tma_a, A, (uint64_t)a_rows, (flags & GF_A_TILED) ? (uint64_t)GEMM_BK : (uint64_t)K, (uint64_t)lda, GEMM_BM);
     if (rc) return rc;

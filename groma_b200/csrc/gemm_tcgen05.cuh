@@ -13,7 +13,12 @@ namespace gb {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_MAX_TAPS = 27;
-constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA, warps 2..5 epilogue (tiles narrower than 128 columns)
+// Wide tiles (BN >= 128) run EIGHT epilogue warps: two per TMEM lane quarter, each draining half of the tile's columns.  With one
+// epilogue warp per SM sub-partition the 128 x 256 tile of a K = 1024 GEMM (ViT) took longer to drain (bias + erf-GELU + pack +
+// store ~ 9 k cycles) than its 16 k-blocks take on the tensor pipe (8 k cycles): 43.7 % tensor-active (profiles/r01_gemm_k1024_AFTER.md).
+__host__ __device__ constexpr int gemm_epi_warps(int bn) { return bn >= 128 ? 8 : 4; }
+__host__ __device__ constexpr int gemm_threads(int bn) { return 64 + 32 * gemm_epi_warps(bn); }
 
 enum GemmAct : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_SWIGLU = 3 };
 enum GemmFlags : int {
@@ -58,7 +63,9 @@ struct GemmCfg {
 #endif
     static constexpr int STAGES = (CG == 2) ? 6 : ((BN >= 256) ? 4 : (BN >= 128 ? 6 : (BN == 16 ? GROMA_BN16_STAGES : 8)));
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * (32 * 80 + 32 * 8) /*epilogue staging*/;
+    static constexpr int EPW = gemm_epi_warps(BN);
+    static constexpr int THREADS = gemm_threads(BN);
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPW * (32 * 80 + 32 * 8) /*epilogue staging*/;
 };
 
 // Grouped rasterisation: consecutive tiles walk GROUP_M m-blocks before advancing n, so the ~148 tiles in flight share
@@ -87,7 +94,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // single-CTA 128x256 tile) and the ring deepens from 4 to 6 stages.  Leader CTA (rank 0) issues the MMAs; barriers:
 // full (leader, one arrive per CTA + all TMA bytes), empty / tmem_full (both CTAs, multicast commit), tmem_empty (leader).
 template <int BN, int CG>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(gemm_threads(BN), 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     using Cfg = GemmCfg<BN, CG>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -125,7 +132,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
             }
             for (int i = 0; i < 2; ++i) {
                 mbar_init(&tfull_bar[i], 1);
-                mbar_init(&tempty_bar[i], 4 * CG);  // one arrive per epilogue warp (of both CTAs)
+                mbar_init(&tempty_bar[i], Cfg::EPW * CG);  // one arrive per epilogue warp (of both CTAs)
             }
             fence_barrier_init();
         }
@@ -246,8 +253,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
             }
         }
     } else {
-        // ===================== epilogue warps (2..5) =====================
+        // ===================== epilogue warps (2..5, and 6..9 on wide tiles) =====================
         const int q = warp & 3;  // TMEM lane quarter this warp may access
+        constexpr int EPH = Cfg::EPW / 4;                 // warps sharing a lane quarter: each drains BN / EPH columns
+        const int col_lo = ((warp - 2) >> 2) * (BN / EPH), col_hi = col_lo + BN / EPH;
         int acc = 0;
         uint32_t acc_phase = 0;
         const bool out_f32 = (p.flags & GF_OUT_F32) != 0;
@@ -283,7 +292,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
             long long* stg_rows = reinterpret_cast<long long*>(stg + 32 * 80);
             if (staged) stg_rows[lane] = row_ok ? out_row : -1;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += CHUNK) {
+            for (int c0 = col_lo; c0 < col_hi; c0 += CHUNK) {
                 uint32_t v[32];
                 const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + c0);
                 __syncwarp();  // tcgen05.ld is .sync.aligned (and orders the staging buffer reuse)
@@ -439,6 +448,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
             // ---- fused split-K finish: the last CTA to deliver a partial of this tile sums all splits (fixed order, so the
             //      result is deterministic) and runs the epilogue -- no separate reduce launch on the decode path
             if (partial && p.tile_counters != nullptr) {
+                // (host side refuses tile_counters for tiles >= 128 columns: this finish assumes the 128-thread epilogue of narrow tiles)
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);   // TMEM no longer needed: let the MMA warp run ahead

@@ -422,9 +422,10 @@ def vit_embed(patch: torch.Tensor, cls: torch.Tensor, pos: torch.Tensor, B: int,
     return out
 
 
-def mean_tokens(ts: Sequence[torch.Tensor], skip: int) -> torch.Tensor:
+def mean_tokens(ts: Sequence[torch.Tensor], skip: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     B, T, C = ts[0].shape
-    out = torch.empty((B, T - skip, C), dtype=torch.bfloat16, device=ts[0].device)
+    if out is None:
+        out = torch.empty((B, T - skip, C), dtype=torch.bfloat16, device=ts[0].device)
     ptrs = [_p(t) for t in ts] + [None] * (4 - len(ts))
     _chk(_L().groma_mean_tokens(ptrs[0], ptrs[1], ptrs[2], ptrs[3], len(ts), _p(out), B, T, C, skip, _stream()),
          "groma_mean_tokens")

@@ -99,6 +99,8 @@ def run_fullsize_check(model, cfg, sd_f32: Dict[str, torch.Tensor], tok, n_text:
     res["dec_last_nrel"] = nrel(eng.stages["dec_last"], ob.stages["dec_last"])
     res["pred_boxes_max_abs"] = (pc2.cpu()[:, :Q] - want["pred_boxes"]).abs().max().item()
     res["scores_max_abs"] = (sc2.cpu()[:, :Q] - want["scores"]).abs().max().item()
+    res["pred_boxes_rms_abs"] = (pc2.cpu()[:, :Q] - want["pred_boxes"]).pow(2).mean().sqrt().item()
+    res["scores_rms_abs"] = (sc2.cpu()[:, :Q] - want["scores"]).pow(2).mean().sqrt().item()
     # NMS on the teacher-forced proposals vs the oracle's keep list on ITS proposals (equal unless a score gap / IoU sits inside bf16 noise)
     torch.manual_seed(1234)
     sel_tf = eng.select_regions(pc2.clone(), px2.clone(), sc2.clone(), None, None, cfg.nms_thres, cfg.box_score_thres, cfg.max_region_num)
@@ -163,6 +165,8 @@ def run_fullsize_check(model, cfg, sd_f32: Dict[str, torch.Tensor], tok, n_text:
         fl["ref_init_max_abs"] = (ob.stages["ref_init"] - of.stages["ref_init"]).abs().max().item()
         fl["pred_boxes_max_abs"] = (want["pred_boxes"] - wf["pred_boxes"]).abs().max().item()
         fl["scores_max_abs"] = (want["scores"] - wf["scores"]).abs().max().item()
+        fl["pred_boxes_rms_abs"] = (want["pred_boxes"] - wf["pred_boxes"]).pow(2).mean().sqrt().item()
+        fl["scores_rms_abs"] = (want["scores"] - wf["scores"]).pow(2).mean().sqrt().item()
         fl["logits_nrel_all_positions"] = nrel(want["logits"], wf["logits"])
         fl["logits_nrel_last_position"] = nrel(want["logits"][:, -1], wf["logits"][:, -1])
         fl["logits_rms"] = rmsrel(want["logits"], wf["logits"])
@@ -180,7 +184,10 @@ def run_fullsize_check(model, cfg, sd_f32: Dict[str, torch.Tensor], tok, n_text:
 # the same points but accumulate fp32 sums in a different order decorrelate to that same level within a few layers (one 1-ulp
 # flip of a GEMM input re-rolls ~13% of the next layer's roundings), so BASELINE.json's 1e-3 is a per-op figure (asserted with
 # fp32 outputs in tests/test_ops_gpu.py at 2e-5), not an end-to-end one.
-BARS = {"floor_factor": 1.5, "eps": 2e-3, "token_margin_rel": 1e-2}
+# `*_max_abs` statistics are maxima over the 1200 box coordinates / 300 scores of decoder states that themselves sit 4-6e-2 from
+# their fp32 values: heavy-tailed (a query whose reference box lies near the inverse-sigmoid clamp amplifies its state's error),
+# so they get MAX_FACTOR; their `*_rms_abs` twins and every norm-relative stage distance get FLOOR_FACTOR.
+BARS = {"floor_factor": 1.5, "max_factor": 4.0, "eps": 2e-3, "token_margin_rel": 1e-2}
 EXACT = ("topk_is_stable_argsort_of_own_scores", "nms_keep_exact_on_own_proposals", "selected_boxes_exact_on_own_proposals", "assembled_ids_exact")
 
 
@@ -196,9 +203,10 @@ def verdict(res: dict) -> list:
             got = res["logits_rms_vs_bf16_oracle"]
         else:
             got = res[k]
-        lim = BARS["floor_factor"] * f + BARS["eps"]
+        fac = BARS["max_factor"] if k.endswith("_max_abs") else BARS["floor_factor"]
+        lim = fac * f + BARS["eps"]
         if got > lim:
-            bad.append(f"{k}: gpu-vs-bf16-oracle {got:.3e} > {BARS['floor_factor']} x floor {f:.3e} + {BARS['eps']}")
+            bad.append(f"{k}: gpu-vs-bf16-oracle {got:.3e} > {fac} x floor {f:.3e} + {BARS['eps']}")
     if res["topk_overlap_with_oracle"] < 0.9:
         bad.append(f"two-stage top-k overlap with the oracle {res['topk_overlap_with_oracle']:.3f} < 0.9")
     if not res["tokens_equal"] and res["tokens_divergence_oracle_margin_rel"] >= BARS["token_margin_rel"]:

@@ -86,20 +86,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
-// 2^x on the FMA / integer pipes (no MUFU): x = n + f with n = round(x) by the 1.5*2^23 magic add, f in [-0.5, 0.5],
-// 2^f by a degree-3 polynomial (max relative error 1.0e-4, twenty times finer than the bf16 the result is rounded to), n added into
-// the exponent field.  MUFU.EX2 runs at 16 / clk / SM on B200: 32 768 exponentials per query-tile pair = 2 048 cycles, as long as the
-// pair's MMAs -- so half of the exponentials go here (FlashAttention-4's trick).  Inputs below -126 are clamped (result ~ 2^-126 ~ 0).
-__device__ __forceinline__ float ex2_poly(float x) {
-    x = fmaxf(x, -126.0f);
-    const float t = x + 12582912.0f;                 // low mantissa bits of t = round-to-nearest(x)
-    const float f = x - (t - 12582912.0f);
-    float p = fmaf(0.05592204f, f, 0.24264008f);
-    p = fmaf(p, f, 0.69312103f);
-    p = fmaf(p, f, 0.99992448f);
-    return __int_as_float(__float_as_int(p) + ((__float_as_int(t) - 0x4B400000) << 23));
-}
-
 template <int D>
 struct FaSmem {
     static constexpr int DBLK = D / 64;                 // 64-column (128-byte) blocks per row of Q/K/V
@@ -313,8 +299,10 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa2q_kernel(const __g
             for (int i = 0; i < 128; i += 8) {
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
-                    const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i + 2 * t]), p.scale_log2, neg_m));      // MUFU pipe
-                    const float p1 = ex2_poly(fmaf(__uint_as_float(sv[i + 2 * t + 1]), p.scale_log2, neg_m));    // FMA + ALU pipes
+                    // (moving half of the exponentials to a degree-3 polynomial on the FMA pipe, FlashAttention-4 style, measured SLOWER
+                    //  here -- 474 -> 394 TFLOP/s: this loop is issue-bound, not MUFU-bound, on B200)
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i + 2 * t]), p.scale_log2, neg_m));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i + 2 * t + 1]), p.scale_log2, neg_m));
                     rs4[t] += p0 + p1;
                     sv[(i >> 1) + t] = pack_bf16x2(p0, p1);
                 }

@@ -380,7 +380,14 @@ class GromaModel(torch.nn.Module):
             d["ids"].copy_(input_ids.reshape(-1).to(eng.dev))
             d["pos"].fill_(past)
             d["kv_len"].fill_(past + 1)               # all-ones mask over past+1 (groma.py:376-379)
-            logits = eng.decode_step(B).clone().reshape(B, 1, -1)
+            # step-wise callers (serve/model_worker.py:288-304, serve/cli.py) get the same CUDA-graph step as generate() from
+            # their second decode step on; the first one runs eagerly (it also warms every kernel up outside the capture)
+            self._fwd_decode_steps = getattr(self, "_fwd_decode_steps", 0) + 1
+            if self.use_cuda_graph and self._fwd_decode_steps >= 2:
+                self._capture(B).replay()
+                logits = d["logits"].clone().reshape(B, 1, -1)
+            else:
+                logits = eng.decode_step(B).clone().reshape(B, 1, -1)
             eng.check_decode_status()
             eng.past = past + 1
             labels_new = None

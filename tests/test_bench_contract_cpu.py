@@ -12,7 +12,7 @@ def _load(name):
         return json.loads(f.read().strip().splitlines()[-1])
 
 
-@pytest.mark.parametrize("name,n", [("r01_bench_n1.json", 1), ("r01_bench_n2.json", 2)])
+@pytest.mark.parametrize("name,n", [("r01_bench_n1.json", 1), ("r01_bench_n2.json", 2), ("r02_bench_n1.json", 1)])
 def test_product_arm_line(name, n):
     d = _load(name)
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
@@ -30,6 +30,18 @@ def test_product_arm_line(name, n):
     if n == 1:
         b = d["cpu_baseline"]
         assert b["kind"] in ("port", "reference") and b["cores"] >= 1 and b["value"] > 0 and b["sample"]
+    if name.startswith("r02"):
+        # round 2: algorithmic bytes are the section-8(d) ones only (weights), DRAM traffic from the round's ncu capture within 10 %,
+        # every other decode kernel class has its own entry, and the full-size parity check rides in the line with no violation
+        assert r["algorithmic_bytes"].keys() == {"weights"} and 1.0 <= r["traffic"] / r["algorithmic_bytes_per_launch"] < 1.1
+        assert any("decode_attention" in o["kernel"] and 0 < o["frac"] < 1.1 for o in r["other_kernels"])
+        pc = d["parity_check"]
+        assert pc["violations"] == [] and pc["assembled_ids_exact"] and pc["nms_keep_exact_on_own_proposals"] and "floor" in pc
+
+
+def test_reference_arm_line_round2():
+    d = _load("r02_bench_reference_arm.json")
+    assert d["impl"] == "reference" and d["value"] > 0 and d["e2e"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
 
 
 def test_reference_arm_line():

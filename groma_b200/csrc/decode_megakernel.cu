@@ -168,18 +168,36 @@ __device__ __noinline__ void mk_fail(const MkCtx& c, int code, long long a, long
 }
 __device__ __forceinline__ bool mk_aborted(const MkCtx& c) { return *c.abort_s != 0; }
 // returns false when the wait was abandoned
+// mbarrier.try_wait suspends the thread in hardware until the phase completes or a time limit passes -- unlike a test_wait spin it
+// does not keep hammering the shared-memory pipeline the TMA writes and the UMMA operand reads go through (128-256 worker
+// threads parked on a barrier for a whole GEMM phase did exactly that in the first version).
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, 0x989680;\n\t"     // suspend-time hint: 10 ms
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ bool mk_wait_mbar(const MkCtx& c, uint64_t* bar, uint32_t parity, int code, long long info) {
     if (mbar_test(bar, parity)) return true;
     if (mk_aborted(c)) return false;
     const unsigned long long t0 = mk_now();
-    int spins = 0;
-    while (!mbar_test(bar, parity)) {
-        if ((++spins & 255) == 0) {
-            if (mk_aborted(c) || ld_relaxed(c.p->status) != 0) { mk_note(c, code, info, parity); *c.abort_s = 1; return false; }
-            if (mk_now() - t0 > MK_TIMEOUT_NS) { mk_fail(c, code, info, parity); return false; }
-        }
+    while (!mbar_try(bar, parity)) {
+        if (mk_aborted(c) || ld_relaxed(c.p->status) != 0) { mk_note(c, code, info, parity); *c.abort_s = 1; return false; }
+        if (mk_now() - t0 > MK_TIMEOUT_NS) { mk_fail(c, code, info, parity); return false; }
     }
     return true;
+}
+// warp-collective form: lane 0 waits, the warp re-converges, every lane then observes the (already completed) phase itself so that
+// the asynchronous-proxy writes the barrier tracks are visible to it
+__device__ __forceinline__ bool mk_wait_mbar_warp(const MkCtx& c, uint64_t* bar, uint32_t parity, int code, long long info) {
+    bool ok = true;
+    if ((threadIdx.x & 31) == 0) ok = mk_wait_mbar(c, bar, parity, code, info);
+    ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+    if (ok) ok = mbar_test(bar, parity);
+    return ok;
 }
 __device__ __forceinline__ bool mk_wait_flag(const MkCtx& c, const int* flag, int need, int code, long long info) {
     if (ld_acquire(flag) >= need) return true;
@@ -543,7 +561,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_megakernel(const __
                 const int tile = u / g.kb;
                 const int uend = min(g.u1, (tile + 1) * g.kb);
                 if (w < 4) {
-                    bool okw = ok && mk_wait_mbar(ctx, &T.tfull_bar[acc], acc_phase, 301, tile);
+                    bool okw = mk_wait_mbar_warp(ctx, &T.tfull_bar[acc], acc_phase, 301, tile) && ok;
                     okw = __all_sync(0xffffffffu, okw);
                     if (okw) {
                         tc_fence_after();
@@ -697,7 +715,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_megakernel(const __
                         // ---- K slot: 4 keys per half-warp (key j = hw + 16*u)
                         {
                             const int s = seq % MK_STAGES;
-                            ok = ok && mk_wait_mbar(ctx, &T.full_bar[s], (uint32_t)((seq / MK_STAGES) & 1), 504, seq);
+                            ok = mk_wait_mbar_warp(ctx, &T.full_bar[s], (uint32_t)((seq / MK_STAGES) & 1), 504, seq) && ok;
                             const __nv_bfloat16* ks = reinterpret_cast<const __nv_bfloat16*>(smem + s * MK_STAGE_BYTES);
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
@@ -725,7 +743,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_megakernel(const __
                         // ---- V slot
                         {
                             const int s = seq % MK_STAGES;
-                            ok = ok && mk_wait_mbar(ctx, &T.full_bar[s], (uint32_t)((seq / MK_STAGES) & 1), 505, seq);
+                            ok = mk_wait_mbar_warp(ctx, &T.full_bar[s], (uint32_t)((seq / MK_STAGES) & 1), 505, seq) && ok;
                             const __nv_bfloat16* vs = reinterpret_cast<const __nv_bfloat16*>(smem + s * MK_STAGE_BYTES);
                             uint4 vv[4];
 #pragma unroll

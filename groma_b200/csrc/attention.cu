@@ -498,16 +498,26 @@ __global__ void __cluster_dims__(DEC_SPLIT, 1, 1) __launch_bounds__((DEC_WARPS +
             constexpr int half = D / 2;
             const int j = threadIdx.x;                       // one rotary pair (j, j + half) per consumer thread
             const int N = 3 * H * D;
+            // every partial of q (and k, v in the appending CTA) is in flight before the first add, and behind the position load:
+            // the prologue costs two L2 round trips (pos -> cos/sin) instead of 1 + S (+ 2S)
             const int pos = *ra.pos_ptr;
+            const int cols[3] = {h * D, H * D + h * D, 2 * H * D + h * D};
+            float s1[3], s2[3];
+            if (append) {
+                splitk_pairs<3>(ra.ws, ra.S, (int)gridDim.y, N, b, cols, j, half, s1, s2);
+            } else {
+                const int c0[1] = {cols[0]};
+                float t1[1], t2[1];
+                splitk_pairs<1>(ra.ws, ra.S, (int)gridDim.y, N, b, c0, j, half, t1, t2);
+                s1[0] = t1[0]; s2[0] = t2[0];
+            }
             const float c = ra.cos_t[(long long)pos * half + j], sn = ra.sin_t[(long long)pos * half + j];
-            float q1, q2;
-            splitk_pair(ra.ws, ra.S, (int)gridDim.y, N, b, h * D, j, half, q1, q2);
+            float q1 = s1[0], q2 = s2[0];
             q1 = bf16_round(q1); q2 = bf16_round(q2);
             rope_pair(q1, q2, c, sn, s_new[0][j], s_new[0][j + half]);
             if (append) {
-                float k1, k2, v1, v2;
-                splitk_pair(ra.ws, ra.S, (int)gridDim.y, N, b, H * D + h * D, j, half, k1, k2);
-                splitk_pair(ra.ws, ra.S, (int)gridDim.y, N, b, 2 * H * D + h * D, j, half, v1, v2);
+                float k1 = s1[1], k2 = s2[1];
+                const float v1 = s1[2], v2 = s2[2];
                 k1 = bf16_round(k1); k2 = bf16_round(k2);
                 rope_pair(k1, k2, c, sn, s_new[1][j], s_new[1][j + half]);
                 s_new[2][j] = __float2bfloat16_rn(v1);

@@ -1,5 +1,6 @@
 // Data-movement / pointwise kernels of the Groma forward path (all HBM-bound; 16-byte vectors, grid-stride).
 #include "ptx.cuh"
+#include "decode_common.cuh"
 #include "capi_common.h"
 
 namespace gb {
@@ -193,10 +194,15 @@ __global__ void rope_kv_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloa
         for (int u = 0; u < 4; ++u) {
             const float2 a = __bfloat1622float2(q1[u]), bq = __bfloat1622float2(q2[u]);
             const float2 e = __bfloat1622float2(k1[u]), f = __bfloat1622float2(k2[u]);
-            qa[u] = pack_bf16x2(a.x * c[2 * u] - bq.x * s[2 * u], a.y * c[2 * u + 1] - bq.y * s[2 * u + 1]);
-            qb[u] = pack_bf16x2(bq.x * c[2 * u] + a.x * s[2 * u], bq.y * c[2 * u + 1] + a.y * s[2 * u + 1]);
-            ka[u] = pack_bf16x2(e.x * c[2 * u] - f.x * s[2 * u], e.y * c[2 * u + 1] - f.y * s[2 * u + 1]);
-            kb[u] = pack_bf16x2(f.x * c[2 * u] + e.x * s[2 * u], f.y * c[2 * u + 1] + e.y * s[2 * u + 1]);
+            __nv_bfloat16 r[8];
+            rope_pair(a.x, bq.x, c[2 * u], s[2 * u], r[0], r[2]);
+            rope_pair(a.y, bq.y, c[2 * u + 1], s[2 * u + 1], r[1], r[3]);
+            rope_pair(e.x, f.x, c[2 * u], s[2 * u], r[4], r[6]);
+            rope_pair(e.y, f.y, c[2 * u + 1], s[2 * u + 1], r[5], r[7]);
+            qa[u] = (uint32_t)__bfloat16_as_ushort(r[0]) | ((uint32_t)__bfloat16_as_ushort(r[1]) << 16);
+            qb[u] = (uint32_t)__bfloat16_as_ushort(r[2]) | ((uint32_t)__bfloat16_as_ushort(r[3]) << 16);
+            ka[u] = (uint32_t)__bfloat16_as_ushort(r[4]) | ((uint32_t)__bfloat16_as_ushort(r[5]) << 16);
+            kb[u] = (uint32_t)__bfloat16_as_ushort(r[6]) | ((uint32_t)__bfloat16_as_ushort(r[7]) << 16);
         }
         __nv_bfloat16* qo = q_out + ((long long)b * T + t) * H * D + h * D + j;
         *reinterpret_cast<uint4*>(qo) = make_uint4(qa[0], qa[1], qa[2], qa[3]);

@@ -138,7 +138,13 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, i
         }
         const int m = i / N, n = i - (long long)m * N;
         float v = 0.f;
-        for (int s = 0; s < splits; ++s) v += ws[((long long)s * M + m) * N + n];
+        for (int s0 = 0; s0 < splits; s0 += 8) {   // all partial loads of a batch in flight before the first add (same add order)
+            float t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) if (s0 + u < splits) t[u] = ws[((long long)(s0 + u) * M + m) * N + n];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) if (s0 + u < splits) v += t[u];
+        }
         if (bias) v += bias[bias_m ? m : n];
         v = apply_act(v, act);
         if (gamma) v *= gamma[bias_m ? m : n];
@@ -153,13 +159,21 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, i
 
 using namespace gb;
 
-GROMA_API int32_t groma_gemm_bf16(const void* A, int64_t a_rows, int64_t lda, const void* B, int64_t b_rows,
-                                   int64_t ldb, int32_t M, int32_t N, int32_t K, int32_t num_taps,
-                                   const int32_t* a_row_off, void* out, int64_t ld_m, int64_t ld_n, int32_t flags,
-                                   int32_t act, const float* bias, const float* gamma, const void* residual,
-                                   float* ws, int32_t split_k, int32_t* tile_counters, int32_t conv_hp, int32_t conv_wp,
-                                   int32_t block_n, void* stream) {
+namespace {
+struct RopeEpilogue {   // GF_ROPE_QKV operands (see GemmParams)
+    const float* cos_t; const float* sin_t; void* cache_k; void* cache_v;
+    int T, H, pos0; long long cap;
+};
+}  // namespace
+
+static int32_t gemm_impl(const void* A, int64_t a_rows, int64_t lda, const void* B, int64_t b_rows,
+                         int64_t ldb, int32_t M, int32_t N, int32_t K, int32_t num_taps,
+                         const int32_t* a_row_off, void* out, int64_t ld_m, int64_t ld_n, int32_t flags,
+                         int32_t act, const float* bias, const float* gamma, const void* residual,
+                         float* ws, int32_t split_k, int32_t* tile_counters, int32_t conv_hp, int32_t conv_wp,
+                         int32_t block_n, void* stream, const RopeEpilogue* rope) {
     if (!A || !B || M <= 0 || N <= 0 || K <= 0) return GROMA_ERR_ARG;
+    if (((flags & GF_ROPE_QKV) != 0) != (rope != nullptr)) return GROMA_ERR_ARG;
     if (num_taps < 1 || num_taps > GEMM_MAX_TAPS) return GROMA_ERR_ARG;
     if ((lda & 7) || (ldb & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
         return GROMA_ERR_ALIGN;
@@ -198,6 +212,13 @@ GROMA_API int32_t groma_gemm_bf16(const void* A, int64_t a_rows, int64_t lda, co
     p.out = out; p.ld_m = ld_m; p.ld_n = ld_n;
     p.bias = bias; p.gamma = gamma; p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
     p.ws = ws; p.conv_hp = conv_hp; p.conv_wp = conv_wp; p.tile_counters = tile_counters;
+    p.rope_cos = p.rope_sin = nullptr; p.rope_k = p.rope_v = nullptr; p.rope_T = 1; p.rope_H = 1; p.rope_pos0 = 0; p.rope_cap = 0;
+    if (rope) {
+        if (bn != 256 && bn != 512) return GROMA_ERR_UNSUPPORTED;   // one head (128 columns) per epilogue warp needs the 256-wide tile
+        p.rope_cos = rope->cos_t; p.rope_sin = rope->sin_t;
+        p.rope_k = reinterpret_cast<__nv_bfloat16*>(rope->cache_k); p.rope_v = reinterpret_cast<__nv_bfloat16*>(rope->cache_v);
+        p.rope_T = rope->T; p.rope_H = rope->H; p.rope_pos0 = rope->pos0; p.rope_cap = rope->cap;
+    }
     {
         // early release of the dependent grid (measured: decode step 4.49 -> 4.40 ms); GROMA_GEMM_EARLY_TRIGGER=0 disables
         static const int early = [] { const char* e = getenv("GROMA_GEMM_EARLY_TRIGGER"); return e ? atoi(e) : 1; }();
@@ -216,6 +237,38 @@ GROMA_API int32_t groma_gemm_bf16(const void* A, int64_t a_rows, int64_t lda, co
         case 256: return launch_gemm<256>(p, st);
         default: return GROMA_ERR_ARG;
     }
+}
+
+GROMA_API int32_t groma_gemm_bf16(const void* A, int64_t a_rows, int64_t lda, const void* B, int64_t b_rows,
+                                   int64_t ldb, int32_t M, int32_t N, int32_t K, int32_t num_taps,
+                                   const int32_t* a_row_off, void* out, int64_t ld_m, int64_t ld_n, int32_t flags,
+                                   int32_t act, const float* bias, const float* gamma, const void* residual,
+                                   float* ws, int32_t split_k, int32_t* tile_counters, int32_t conv_hp, int32_t conv_wp,
+                                   int32_t block_n, void* stream) {
+    if (flags & GF_ROPE_QKV) return GROMA_ERR_ARG;   // that epilogue has its own entry point below
+    return gemm_impl(A, a_rows, lda, B, b_rows, ldb, M, N, K, num_taps, a_row_off, out, ld_m, ld_n, flags, act, bias, gamma,
+                     residual, ws, split_k, tile_counters, conv_hp, conv_wp, block_n, stream, nullptr);
+}
+
+// LLaMA attention input in one launch: x [B*T, K] @ Wqkv^T [3*H*128, K] with rotate-half RoPE on q/k and the KV-cache
+// append done by the GEMM epilogue (replaces q_proj/k_proj/v_proj + apply_rotary_pos_emb + the cache torch.cat of
+// $HF/models/llama/modeling_llama.py:199-246).  q_out [B*T, H*128]; cache_k/v [B, H, ctx_cap, 128]; token t of every
+// sequence sits at position pos0 + t.  block_n: 256 (one CTA per tile) or 512 (cta_group::2 pair).
+GROMA_API int32_t groma_gemm_qkv_rope(const void* x, int64_t ldx, const void* w_qkv, int64_t ldw, int32_t B, int32_t T,
+                                       int32_t H, int32_t D, int32_t K, void* q_out, void* cache_k, void* cache_v,
+                                       const float* cos_t, const float* sin_t, int32_t pos0, int64_t ctx_cap,
+                                       int32_t block_n, void* stream) {
+    if (!x || !w_qkv || !q_out || !cache_k || !cache_v || !cos_t || !sin_t) return GROMA_ERR_ARG;
+    if (B <= 0 || T <= 0 || H <= 0 || K <= 0 || pos0 < 0 || (long long)pos0 + T > ctx_cap) return GROMA_ERR_ARG;
+    if (D != 128 || (H & 1)) return GROMA_ERR_UNSUPPORTED;          // 3*H*128 must tile by 256 columns
+    if (block_n != 256 && block_n != 512) return GROMA_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(q_out) | reinterpret_cast<uintptr_t>(cache_k) | reinterpret_cast<uintptr_t>(cache_v) |
+         reinterpret_cast<uintptr_t>(cos_t) | reinterpret_cast<uintptr_t>(sin_t)) & 15) return GROMA_ERR_ALIGN;
+    RopeEpilogue r{cos_t, sin_t, cache_k, cache_v, T, H, pos0, (long long)ctx_cap};
+    const long long M = (long long)B * T;
+    if (M > 0x7fffffffLL) return GROMA_ERR_ARG;
+    return gemm_impl(x, M, ldx, w_qkv, 3LL * H * D, ldw, (int32_t)M, 3 * H * D, K, 1, nullptr, q_out, (int64_t)H * D, 1,
+                     GF_ROPE_QKV, ACT_NONE, nullptr, nullptr, nullptr, nullptr, 1, nullptr, 0, 0, block_n, stream, &r);
 }
 
 GROMA_API int32_t groma_splitk_reduce(const float* ws, int32_t splits, int32_t M, int32_t N, int32_t act,

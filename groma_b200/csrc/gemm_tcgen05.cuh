@@ -7,6 +7,7 @@
 // (each tap is a row shift of A and a K offset of B), see DESIGN.md "conv as shifted-row GEMM".
 #pragma once
 #include "ptx.cuh"
+#include "decode_common.cuh"
 
 namespace gb {
 
@@ -30,6 +31,7 @@ enum GemmFlags : int {
     GF_A_TILED = 32,      // A is pre-tiled in HBM: [m_tile][k_block][128 rows][64 cols] -> every TMA load is one contiguous 16 KB
     GF_PDL = 64,          // launched with programmatic stream serialisation: A (weights) is prefetched before griddepcontrol.wait
     GF_PARTIAL_T = 128,   // with GF_PARTIAL: partials stored transposed, ws[split][n][m] (swap-AB decode: token-major rows)
+    GF_ROPE_QKV = 256,    // fused LLaMA qkv projection: rotate q/k (RoPE) in the epilogue, q -> out, k/v -> the KV cache (256-wide tiles, D = 128)
 };
 
 struct GemmParams {
@@ -50,6 +52,13 @@ struct GemmParams {
     int conv_hp, conv_wp;  // padded map dims for GF_CONV_ROWS
     int* tile_counters;    // GF_PARTIAL + non-null: the CTA that completes a tile's last split reduces ws and runs the epilogue
     int early_trigger;     // GF_PDL: release the dependent grid at kernel start (it parks at its own griddepcontrol.wait)
+    // GF_ROPE_QKV: rows = (sequence b, token t) with t < rope_T; columns = [q | k | v] x [rope_H heads] x [128]
+    const float* rope_cos;  // fp32 [max_pos, 64]
+    const float* rope_sin;
+    __nv_bfloat16* rope_k;  // KV cache [B, rope_H, rope_cap, 128]
+    __nv_bfloat16* rope_v;
+    int rope_T, rope_H, rope_pos0;
+    long long rope_cap;
 };
 
 template <int BN, int CG = 1>
@@ -291,8 +300,70 @@ __global__ void __launch_bounds__(gemm_threads(BN), 1) gemm_bf16_tcgen05_kernel(
             uint8_t* stg = stage_base + (warp - 2) * STG_WARP_BYTES;
             long long* stg_rows = reinterpret_cast<long long*>(stg + 32 * 80);
             if (staged) stg_rows[lane] = row_ok ? out_row : -1;
+            int c_first = col_lo;
+            if constexpr (BN == 256 && Cfg::EPW == 8) {
+                if (p.flags & GF_ROPE_QKV) {
+                    // This warp's 128 columns are exactly one head of q, k or v.  The projection is rounded to bf16 first (what the
+                    // unfused path stored before rope_kv_kernel re-read it), q/k are rotated in fp32 with the pair (j, j + 64)
+                    // ($HF/models/llama/modeling_llama.py:138-168), and the row goes straight to q_out / the KV cache: the
+                    // [B*T, 3*H*D] intermediate and its second pass over HBM are gone.
+                    c_first = col_hi;
+                    const int nh = n_blk * BN + col_lo;
+                    const int HD = p.rope_H << 7;
+                    const int which = nh / HD;                       // 0 = q, 1 = k, 2 = v
+                    const int head = (nh - which * HD) >> 7;
+                    const int bb = row / p.rope_T, tt = row - bb * p.rope_T;
+                    const int pos = p.rope_pos0 + tt;
+                    __nv_bfloat16* dst = (which == 0)
+                        ? reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * HD + (head << 7)
+                        : (which == 1 ? p.rope_k : p.rope_v) + ((((long long)bb * p.rope_H + head) * p.rope_cap + pos) << 7);
+                    const float* cs = p.rope_cos + (long long)pos * 64;
+                    const float* sn = p.rope_sin + (long long)pos * 64;
 #pragma unroll 1
-            for (int c0 = col_lo; c0 < col_hi; c0 += CHUNK) {
+                    for (int cc = 0; cc < 2; ++cc) {
+                        uint32_t v1[32], v2[32];
+                        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + col_lo + 32 * cc);
+                        __syncwarp();
+                        tmem_ld32(taddr, v1);
+                        tmem_ld32(taddr + 64, v2);
+                        tmem_ld_wait();
+                        if (!row_ok || nh >= p.N) continue;
+                        uint32_t o1[16], o2[16];
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float x1[4], x2[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                x1[u] = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v1[j + u])));
+                                x2[u] = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v2[j + u])));
+                            }
+                            __nv_bfloat16 r1[4], r2[4];
+                            if (which < 2) {
+                                const float4 c4 = *reinterpret_cast<const float4*>(cs + 32 * cc + j);
+                                const float4 s4 = *reinterpret_cast<const float4*>(sn + 32 * cc + j);
+                                rope_pair(x1[0], x2[0], c4.x, s4.x, r1[0], r2[0]);
+                                rope_pair(x1[1], x2[1], c4.y, s4.y, r1[1], r2[1]);
+                                rope_pair(x1[2], x2[2], c4.z, s4.z, r1[2], r2[2]);
+                                rope_pair(x1[3], x2[3], c4.w, s4.w, r1[3], r2[3]);
+                            } else {
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) { r1[u] = __float2bfloat16_rn(x1[u]); r2[u] = __float2bfloat16_rn(x2[u]); }
+                            }
+                            o1[j >> 1] = (uint32_t)__bfloat16_as_ushort(r1[0]) | ((uint32_t)__bfloat16_as_ushort(r1[1]) << 16);
+                            o1[(j >> 1) + 1] = (uint32_t)__bfloat16_as_ushort(r1[2]) | ((uint32_t)__bfloat16_as_ushort(r1[3]) << 16);
+                            o2[j >> 1] = (uint32_t)__bfloat16_as_ushort(r2[0]) | ((uint32_t)__bfloat16_as_ushort(r2[1]) << 16);
+                            o2[(j >> 1) + 1] = (uint32_t)__bfloat16_as_ushort(r2[2]) | ((uint32_t)__bfloat16_as_ushort(r2[3]) << 16);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            *reinterpret_cast<uint4*>(dst + 32 * cc + 2 * j) = make_uint4(o1[j], o1[j + 1], o1[j + 2], o1[j + 3]);
+                            *reinterpret_cast<uint4*>(dst + 64 + 32 * cc + 2 * j) = make_uint4(o2[j], o2[j + 1], o2[j + 2], o2[j + 3]);
+                        }
+                    }
+                }
+            }
+#pragma unroll 1
+            for (int c0 = c_first; c0 < col_hi; c0 += CHUNK) {
                 uint32_t v[32];
                 const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + c0);
                 __syncwarp();  // tcgen05.ld is .sync.aligned (and orders the staging buffer reuse)

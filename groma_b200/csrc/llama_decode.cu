@@ -32,7 +32,7 @@ __device__ __forceinline__ float block_sum_f(float v, float* red) {
 
 // x[b,:] = bf16(sum_s ws[s][b][:] + x[b,:]);  y[b,:] = w * bf16(x * rsqrt(mean(x^2)+eps)).  One CTA per token, N % 4 == 0.
 template <int VPT>
-__global__ void reduce_residual_rmsnorm_kernel(const float* __restrict__ ws, int S, int B, int N, __nv_bfloat16* __restrict__ x,
+__global__ void __launch_bounds__(1024) reduce_residual_rmsnorm_kernel(const float* __restrict__ ws, int S, int B, int N, __nv_bfloat16* __restrict__ x,
                                                const float* __restrict__ w, __nv_bfloat16* __restrict__ y, float eps) {
     pdl_trigger();
     pdl_wait();
@@ -46,10 +46,8 @@ __global__ void reduce_residual_rmsnorm_kernel(const float* __restrict__ ws, int
         const int v = threadIdx.x + i * blockDim.x;
         h[i][0] = h[i][1] = h[i][2] = h[i][3] = 0.f;
         if (v < nvec) {
-            for (int s = 0; s < S; ++s) {
-                const float4 t = __ldcg(reinterpret_cast<const float4*>(ws + ((long long)s * B + b) * N + v * 4));
-                h[i][0] += t.x; h[i][1] += t.y; h[i][2] += t.z; h[i][3] += t.w;
-            }
+            const float4 t = splitk_sum4<4>(ws + (long long)b * N + v * 4, (long long)B * N, S);   // 1024-thread blocks: keep the register budget
+            h[i][0] = t.x; h[i][1] = t.y; h[i][2] = t.z; h[i][3] = t.w;
             __nv_bfloat16* xp = x + (long long)b * N + v * 4;
             const uint2 xr = *reinterpret_cast<const uint2*>(xp);
             const float2 x01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xr.x));
@@ -96,10 +94,8 @@ reduce_residual_rmsnorm_cluster_kernel(const float* __restrict__ ws, int S, int 
     const bool act = v * 4 < slice;
     float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f;
     if (act) {
-        for (int s = 0; s < S; ++s) {
-            const float4 t = __ldcg(reinterpret_cast<const float4*>(ws + ((long long)s * B + b) * N + col));
-            h0 += t.x; h1 += t.y; h2 += t.z; h3 += t.w;
-        }
+        const float4 t = splitk_sum4(ws + (long long)b * N + col, (long long)B * N, S);
+        h0 = t.x; h1 = t.y; h2 = t.z; h3 = t.w;
         __nv_bfloat16* xp = x + (long long)b * N + col;
         const uint2 xr = *reinterpret_cast<const uint2*>(xp);
         const float2 x01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xr.x));
@@ -135,11 +131,7 @@ __global__ void reduce_swiglu_kernel(const float* __restrict__ ws, int S, int B,
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int b = i / (NO >> 1);
         const int j2 = i - (long long)b * (NO >> 1);
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s = 0; s < S; ++s) {
-            const float4 t = __ldcg(reinterpret_cast<const float4*>(ws + ((long long)s * B + b) * N + j2 * 4));
-            a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
-        }
+        const float4 a = splitk_sum4(ws + (long long)b * N + j2 * 4, (long long)B * N, S);
         *reinterpret_cast<uint32_t*>(out + (long long)b * NO + j2 * 2) = pack_bf16x2(silu(a.x) * a.y, silu(a.z) * a.w);
     }
 }
@@ -160,10 +152,11 @@ __global__ void reduce_rope_kv_kernel(const float* __restrict__ ws, int S, int B
         long long r = i / half;
         const int h = r % H;
         const int b = r / H;
-        float q1, q2, k1, k2, v1, v2;
-        splitk_pair(ws, S, B, N, b, h * D, j, half, q1, q2);
-        splitk_pair(ws, S, B, N, b, H * D + h * D, j, half, k1, k2);
-        splitk_pair(ws, S, B, N, b, 2 * H * D + h * D, j, half, v1, v2);
+        const int cols[3] = {h * D, H * D + h * D, 2 * H * D + h * D};
+        float s1[3], s2[3];
+        splitk_pairs<3>(ws, S, B, N, b, cols, j, half, s1, s2);
+        float q1 = s1[0], q2 = s2[0], k1 = s1[1], k2 = s2[1];
+        const float v1 = s1[2], v2 = s2[2];
         // the un-fused path stores qkv in bf16 before RoPE: keep that rounding point
         q1 = bf16_round(q1); q2 = bf16_round(q2); k1 = bf16_round(k1); k2 = bf16_round(k2);
         const float c = cos_t[(long long)pos * half + j], sn = sin_t[(long long)pos * half + j];
@@ -173,6 +166,89 @@ __global__ void reduce_rope_kv_kernel(const float* __restrict__ ws, int S, int B
         rope_pair(k1, k2, c, sn, cache_k[co + j], cache_k[co + j + half]);
         cache_v[co + j] = __float2bfloat16_rn(v1);
         cache_v[co + j + half] = __float2bfloat16_rn(v2);
+    }
+}
+
+// Tail of the step in one launch (was splitk_reduce + argmax + decode_advance): logits[b, :] = sum_s ws[s][b][:] (split order, so
+// bit-identical to the generic reduce), greedy argmax with torch.argmax's first-index tie-break written to ids[b] in place, and
+// the position / length bookkeeping for the next step.  HA_CL CTAs (one cluster) per row share the vocabulary; the per-CTA
+// candidates meet in rank 0's shared memory through DSMEM.
+constexpr int HA_CL = 8;
+__device__ __forceinline__ void argmax_merge(float& best, int& bi, float ov, int oi) {
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+}
+__global__ void __cluster_dims__(HA_CL, 1, 1) __launch_bounds__(512)
+reduce_head_argmax_cluster_kernel(const float* __restrict__ ws, int S, int B, int V, float* __restrict__ logits,
+                                  long long* __restrict__ ids, int* __restrict__ pos, int* __restrict__ kv_len) {
+    pdl_trigger();
+    cluster_arrive_relaxed();
+    pdl_wait();
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = (int)cluster.block_rank();
+    __shared__ float sv[32];
+    __shared__ int si[32];
+    __shared__ float pv[HA_CL];
+    __shared__ int pi[HA_CL];
+    const int b = blockIdx.y;
+    const int per = (V + HA_CL - 1) / HA_CL;
+    const int lo = crank * per, hi = min(V, lo + per);
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    constexpr int C = 4, U = 8;   // columns per thread per pass x splits in flight
+    for (int c0 = lo + threadIdx.x; c0 < hi; c0 += C * blockDim.x) {
+        float acc[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = 0.f;
+        for (int s0 = 0; s0 < S; s0 += U) {
+            float t[U][C];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const int col = c0 + c * blockDim.x;
+                    if (s0 + u < S && col < hi) t[u][c] = __ldcg(ws + ((long long)(s0 + u) * B + b) * V + col);
+                }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    if (s0 + u < S && c0 + c * blockDim.x < hi) acc[c] += t[u][c];
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int col = c0 + c * blockDim.x;
+            if (col < hi) {
+                logits[(long long)b * V + col] = acc[c];
+                argmax_merge(best, bi, acc[c], col);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) argmax_merge(best, bi, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bi, o));
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sv[w] = best; si[w] = bi; }
+    __syncthreads();
+    cluster_wait();
+    if (w == 0) {
+        const int nw = blockDim.x >> 5;
+        best = l < nw ? sv[l] : -INFINITY;
+        bi = l < nw ? si[l] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) argmax_merge(best, bi, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bi, o));
+        if (l == 0) {
+            *cluster.map_shared_rank(&pv[crank], 0) = best;
+            *cluster.map_shared_rank(&pi[crank], 0) = bi;
+        }
+    }
+    cluster.sync();
+    if (crank == 0 && threadIdx.x == 0) {
+        best = -INFINITY; bi = 0x7fffffff;
+#pragma unroll
+        for (int r = 0; r < HA_CL; ++r) argmax_merge(best, bi, pv[r], pi[r]);
+        ids[b] = bi;
+        kv_len[b] += 1;
+        if (b == 0) *pos += 1;
     }
 }
 
@@ -203,6 +279,13 @@ GROMA_API int32_t groma_decode_reduce_norm(const float* ws, int32_t splits, int3
     if (nvec <= 1024) return launch_pdl(reduce_residual_rmsnorm_kernel<1>, dim3(B), dim3(((nvec + 31) / 32) * 32), st, pdl, ws, splits, B, N, X, w, Y, eps);
     if (nvec <= 4096) return launch_pdl(reduce_residual_rmsnorm_kernel<4>, dim3(B), dim3(1024), st, pdl, ws, splits, B, N, X, w, Y, eps);
     return GROMA_ERR_UNSUPPORTED;
+}
+
+GROMA_API int32_t groma_decode_head_argmax(const float* ws, int32_t splits, int32_t B, int32_t V, float* logits, int64_t* ids,
+                                           int32_t* pos, int32_t* kv_len, int32_t pdl, void* stream) {
+    if (!ws || !logits || !ids || !pos || !kv_len || splits < 1 || B <= 0 || V <= 0) return GROMA_ERR_ARG;
+    return launch_pdl(reduce_head_argmax_cluster_kernel, dim3(HA_CL, B), dim3(512), reinterpret_cast<cudaStream_t>(stream), pdl, ws,
+                      splits, B, V, logits, reinterpret_cast<long long*>(ids), pos, kv_len);
 }
 
 GROMA_API int32_t groma_decode_reduce_swiglu(const float* ws, int32_t splits, int32_t B, int32_t N, void* out, int32_t pdl,

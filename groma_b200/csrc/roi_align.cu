@@ -34,8 +34,9 @@ __device__ __forceinline__ Tap make_tap(float y, float x, int H, int W) {
     return t;
 }
 
+// generic path (adaptive sampling grid, or maps too large for 32-bit element offsets): every thread recomputes every tap.
 // grid (K, PH + 2*pad); block = C/8 threads (each owns 8 channels) -- loops over the PW bins of one output row.
-__global__ void roi_align_nhwc_kernel(const RoiParams p) {
+__global__ void roi_align_nhwc_generic_kernel(const RoiParams p) {
     const int n = blockIdx.x;
     const int yy = blockIdx.y;  // padded row
     const int OW = p.PW + 2 * p.pad;
@@ -100,6 +101,108 @@ __global__ void roi_align_nhwc_kernel(const RoiParams p) {
     }
 }
 
+// Fixed sampling grid (the path Groma takes: sampling_ratio = 2).  ncu on the first version showed the kernel bound by
+// instruction issue, not by its gathers (profiles/r02_region_ops.md: 83 % issue-active, 24 % DRAM, 546 warp instructions per
+// 16-byte output vector): every thread recomputed the tap indices / weights of every sample and spent two instructions per
+// bf16 pair on unpacking plus five on the weighted sum.  Here the PW * gh * gw taps of the output row are computed ONCE per
+// block into shared memory (valid taps packed first, in the reference's (iy, ix) order), the channel loop reads them back as
+// two broadcast LDS.128 per tap, and the weighted sums run as packed fp32x2 FMAs (same rounding and the same order as the
+// scalar form: mul, fma, fma, fma, add per element).
+__global__ void roi_align_nhwc_kernel(const RoiParams p) {
+    extern __shared__ __align__(16) unsigned char roi_smem[];
+    const int n = blockIdx.x;
+    const int yy = blockIdx.y;  // padded row
+    const int OW = p.PW + 2 * p.pad;
+    const int nvec = p.C >> 3;
+    __nv_bfloat16* orow = p.output + (((long long)n * (p.PH + 2 * p.pad) + yy) * OW) * p.C;
+    const int ph = yy - p.pad;
+    if (ph < 0 || ph >= p.PH) {
+        for (int i = threadIdx.x; i < OW * nvec; i += blockDim.x) *reinterpret_cast<uint4*>(orow + (long long)i * 8) = make_uint4(0, 0, 0, 0);
+        return;
+    }
+    const int g = p.sampling_ratio, spb = g * g;           // samples per bin
+    int4* tap_off = reinterpret_cast<int4*>(roi_smem);                       // [PW][spb] element offsets of the four corners
+    float4* tap_w = reinterpret_cast<float4*>(tap_off + p.PW * spb);         // [PW][spb] bilinear weights
+    int* tap_cnt = reinterpret_cast<int*>(tap_w + p.PW * spb);               // [PW] valid taps of the bin
+    const float* r = p.rois + n * 5;
+    const int bi = (int)r[0];
+    if (threadIdx.x < p.PW) {
+        const int pw = threadIdx.x;
+        const float offset = p.aligned ? 0.5f : 0.0f;
+        const float roi_start_w = r[1] * p.spatial_scale - offset;
+        const float roi_start_h = r[2] * p.spatial_scale - offset;
+        const float roi_end_w = r[3] * p.spatial_scale - offset;
+        const float roi_end_h = r[4] * p.spatial_scale - offset;
+        float roi_width = roi_end_w - roi_start_w, roi_height = roi_end_h - roi_start_h;
+        if (!p.aligned) { roi_width = fmaxf(roi_width, 1.f); roi_height = fmaxf(roi_height, 1.f); }
+        const float bin_h = roi_height / (float)p.PH, bin_w = roi_width / (float)p.PW;
+        int cnt = 0;
+        for (int iy = 0; iy < g; ++iy) {
+            const float y = roi_start_h + ph * bin_h + (iy + .5f) * bin_h / (float)g;
+            for (int ix = 0; ix < g; ++ix) {
+                const float x = roi_start_w + pw * bin_w + (ix + .5f) * bin_w / (float)g;
+                const Tap t = make_tap(y, x, p.H, p.W);
+                if (!t.valid) continue;
+                tap_off[pw * spb + cnt] = make_int4((t.y_low * p.W + t.x_low) * p.C, (t.y_low * p.W + t.x_high) * p.C,
+                                                    (t.y_high * p.W + t.x_low) * p.C, (t.y_high * p.W + t.x_high) * p.C);
+                tap_w[pw * spb + cnt] = make_float4(t.w1, t.w2, t.w3, t.w4);
+                ++cnt;
+            }
+        }
+        tap_cnt[pw] = cnt;
+    }
+    if (p.pad) {
+        for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+            *reinterpret_cast<uint4*>(orow + (long long)i * 8) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(orow + ((long long)(OW - 1) * p.C) + i * 8) = make_uint4(0, 0, 0, 0);
+        }
+    }
+    __syncthreads();
+    const float count = (float)max(spb, 1);
+    const bool pow2 = (spb & (spb - 1)) == 0;
+    const float2 inv2 = make_float2(1.0f / count, 1.0f / count);
+    const __nv_bfloat16* in = p.input + (long long)bi * p.H * p.W * p.C;
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+        const __nv_bfloat16* inv = in + v * 8;
+#pragma unroll 2
+        for (int pw = 0; pw < p.PW; ++pw) {
+            float2 acc[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+            const int cnt = tap_cnt[pw];
+            for (int s = 0; s < cnt; ++s) {
+                const int4 o = tap_off[pw * spb + s];
+                const float4 w = tap_w[pw * spb + s];
+                const uint4 a1 = *reinterpret_cast<const uint4*>(inv + o.x);
+                const uint4 a2 = *reinterpret_cast<const uint4*>(inv + o.y);
+                const uint4 a3 = *reinterpret_cast<const uint4*>(inv + o.z);
+                const uint4 a4 = *reinterpret_cast<const uint4*>(inv + o.w);
+                const __nv_bfloat162* b1 = reinterpret_cast<const __nv_bfloat162*>(&a1);
+                const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&a2);
+                const __nv_bfloat162* b3 = reinterpret_cast<const __nv_bfloat162*>(&a3);
+                const __nv_bfloat162* b4 = reinterpret_cast<const __nv_bfloat162*>(&a4);
+                const float2 w1 = make_float2(w.x, w.x), w2 = make_float2(w.y, w.y), w3 = make_float2(w.z, w.z), w4 = make_float2(w.w, w.w);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float2 t = __fmul2_rn(w1, __bfloat1622float2(b1[q]));
+                    t = __ffma2_rn(w2, __bfloat1622float2(b2[q]), t);
+                    t = __ffma2_rn(w3, __bfloat1622float2(b3[q]), t);
+                    t = __ffma2_rn(w4, __bfloat1622float2(b4[q]), t);
+                    acc[q] = __fadd2_rn(acc[q], t);
+                }
+            }
+            if (pow2) {   // x / 2^k == x * 2^-k bit for bit: skip the eight IEEE divisions
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[q] = __fmul2_rn(acc[q], inv2);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { acc[q].x = acc[q].x / count; acc[q].y = acc[q].y / count; }
+            }
+            *reinterpret_cast<uint4*>(orow + ((long long)(pw + p.pad) * p.C) + v * 8) =
+                make_uint4(pack_bf16x2(acc[0].x, acc[0].y), pack_bf16x2(acc[1].x, acc[1].y),
+                           pack_bf16x2(acc[2].x, acc[2].y), pack_bf16x2(acc[3].x, acc[3].y));
+        }
+    }
+}
+
 }  // namespace gb
 using namespace gb;
 
@@ -121,6 +224,12 @@ GROMA_API int32_t groma_roi_align_forward(const void* input, const float* rois, 
     if (threads > 256) threads = 256;
     threads = ((threads + 31) / 32) * 32;
     dim3 grid(K, pooled_h + 2 * p.pad);
-    roi_align_nhwc_kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    const long long tap_bytes = (long long)pooled_w * sampling_ratio * sampling_ratio * 32 + (long long)pooled_w * 4;
+    const bool fixed_grid = sampling_ratio > 0 && tap_bytes <= 40 * 1024 && pooled_w <= threads &&
+                            (long long)H * W * C < (1LL << 31);
+    if (fixed_grid)
+        roi_align_nhwc_kernel<<<grid, threads, (size_t)tap_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    else
+        roi_align_nhwc_generic_kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     return GROMA_LAUNCH_CHECK();
 }

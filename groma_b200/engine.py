@@ -44,6 +44,8 @@ class GromaEngine:
         self.decode_tiled = os.environ.get("GROMA_DECODE_TILED", "0") == "1"   # decode GEMMs stream a tile-major weight copy (+13 GB)
         self._wt: Dict[str, torch.Tensor] = {}
         self.use_2cta = True           # cta_group::2 GEMM for the large prefill projections and 3x3 convs
+        self.fused_head_tail = os.environ.get("GROMA_FUSED_HEAD_TAIL", "1") != "0"   # decode: head reduce + argmax + advance in one launch
+        self.use_fused_rope = os.environ.get("GROMA_FUSED_ROPE", "1") != "0"   # RoPE + KV append in the qkv GEMM epilogue (prefill)
         # tcgen05 flash attention (attention_tcgen05.cu: two query tiles in ping-pong, P in tensor memory) for head dims 64 / 128
         # (DINOv2 and the LLaMA prefill); the mma.sync kernel stays for head dim 32 (Deformable-DETR self-attention) and the
         # miniature test shapes.  GROMA_TC_ATTENTION=0 switches back for A/B runs.
@@ -537,12 +539,18 @@ class GromaEngine:
         # cta_group::2 (256x256 tiles per CTA pair) for the big projections: +4..8 % over the single-CTA tile; the 22016-wide
         # gate/up projection measured 3 % slower with it and keeps the 128x256 tile
         bn2 = 512 if (self.use_2cta and B * T >= 2048 and cfg.llm_hidden >= 2048) else 0
+        # RoPE + KV append in the qkv GEMM epilogue (one launch, no [B*T, 3*hidden] intermediate) whenever the 256-wide tile
+        # applies: head_dim 128 and enough rows to fill the SMs; tiny test configs keep gemm + rope_kv (same values)
+        fused_rope = self.use_fused_rope and hd == 128 and nh % 2 == 0 and (bn2 == 512 or B * T >= 1024)
         for i in range(cfg.llm_layers):
             o = f"llm.{i}."
             y = G.rmsnorm(x, w[o + "ln1"], cfg.rms_eps)
-            qkv = G.gemm(y, w[o + "qkv.w"], block_n=bn2)
             kc, vc = self.kv[i, 0], self.kv[i, 1]
-            G.rope_kv(qkv, q, kc, vc, self.rope_cos, self.rope_sin, B, T, nh, hd, 0)
+            if fused_rope:
+                G.gemm_qkv_rope(y, w[o + "qkv.w"], q, kc, vc, self.rope_cos, self.rope_sin, B, T, nh, hd, 0, block_n=bn2 or 256)
+            else:
+                qkv = G.gemm(y, w[o + "qkv.w"], block_n=bn2)
+                G.rope_kv(qkv, q, kc, vc, self.rope_cos, self.rope_sin, B, T, nh, hd, 0)
             attn = G.attention_tc if (self.use_tc_attention and hd in (64, 128)) else G.attention
             a = attn(q.reshape(B, T, nh, hd), kc, vc, causal=True, scale=1.0 / math.sqrt(hd), kv_len=kv_len, sk=T)
             G.gemm(a.reshape(B * T, nh * hd), w[o + "o.w"], residual=x, out=x, block_n=bn2)
@@ -773,9 +781,12 @@ class GromaEngine:
             nxt = w[f"llm.{i + 1}.ln1"] if i + 1 < cfg.llm_layers else w["llm.norm"]
             G.decode_reduce_norm(ws, x, nxt, y, cfg.rms_eps, pdl=pdl)
         ws = gemm(y, "head.w", sp["head"])
-        G.splitk_reduce(ws, d["logits"])
-        G.argmax(d["logits"], out=d["ids"])
-        G.decode_advance(d["pos"], d["kv_len"])
+        if self.fused_head_tail:
+            G.decode_head_argmax(ws, d["logits"], d["ids"], d["pos"], d["kv_len"], pdl=pdl)   # reduce + argmax + advance, one launch
+        else:
+            G.splitk_reduce(ws, d["logits"])
+            G.argmax(d["logits"], out=d["ids"])
+            G.decode_advance(d["pos"], d["kv_len"])
         return d["logits"]
 
     def _decode_step_unfused(self, B: int) -> torch.Tensor:

@@ -76,6 +76,21 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     return out
 
 
+def gemm_qkv_rope(x: torch.Tensor, w_qkv: torch.Tensor, q_out: torch.Tensor, cache_k: torch.Tensor, cache_v: torch.Tensor,
+                  cos_t: torch.Tensor, sin_t: torch.Tensor, B: int, T: int, H: int, D: int, pos0: int = 0,
+                  block_n: int = 256) -> torch.Tensor:
+    """qkv projection + RoPE + KV-cache append in one GEMM launch (`groma_gemm_qkv_rope`): x [B*T, K], w_qkv [3*H*D, K];
+    q_out [B*T, H*D]; cache_k/v [B, H, cap, D] (views of the engine's KV arena, unit stride over (cap, D))."""
+    _bf16(x, "x"); _bf16(w_qkv, "w_qkv"); _bf16(q_out, "q_out"); _bf16(cache_k, "cache_k"); _bf16(cache_v, "cache_v")
+    _f32(cos_t, "cos_t"); _f32(sin_t, "sin_t")
+    assert x.shape[0] == B * T and w_qkv.shape[0] == 3 * H * D and q_out.is_contiguous()
+    assert cache_k.is_contiguous() and cache_v.is_contiguous() and cache_k.shape[1] == H and cache_k.shape[3] == D
+    rc = _L().groma_gemm_qkv_rope(_p(x), x.stride(0), _p(w_qkv), w_qkv.stride(0), B, T, H, D, x.shape[1], _p(q_out),
+                                  _p(cache_k), _p(cache_v), _p(cos_t), _p(sin_t), pos0, cache_k.shape[2], block_n, _stream())
+    _chk(rc, "groma_gemm_qkv_rope")
+    return q_out
+
+
 def gemm_splitk(a: torch.Tensor, w: torch.Tensor, split_k: int, *, bias=None, act=ACT_NONE, gamma=None, residual=None,
                 out: Optional[torch.Tensor] = None, out_f32: bool = False, ws: Optional[torch.Tensor] = None,
                 block_n: int = 0) -> torch.Tensor:
@@ -518,6 +533,18 @@ def decode_reduce_norm(ws: torch.Tensor, x: torch.Tensor, w: torch.Tensor, y: to
 def decode_reduce_swiglu(ws: torch.Tensor, out: torch.Tensor, pdl: bool = True):
     S, B, N = ws.shape
     _chk(_L().groma_decode_reduce_swiglu(_p(ws), S, B, N, _p(out), 1 if pdl else 0, _stream()), "groma_decode_reduce_swiglu")
+
+
+def decode_head_argmax(ws: torch.Tensor, logits: torch.Tensor, ids: torch.Tensor, pos: torch.Tensor, kv_len: torch.Tensor,
+                       pdl: bool = False) -> torch.Tensor:
+    """ws [S, B, V] fp32 head partials -> logits [B, V] fp32, ids [B] int64 (greedy), pos / kv_len advanced: one launch."""
+    S, B, V = ws.shape
+    _f32(ws, "ws"); _f32(logits, "logits")
+    assert logits.shape == (B, V) and logits.is_contiguous() and ids.dtype == torch.int64 and ids.numel() == B
+    assert pos.dtype == torch.int32 and kv_len.dtype == torch.int32 and kv_len.numel() == B
+    _chk(_L().groma_decode_head_argmax(_p(ws), S, B, V, _p(logits), _p(ids), _p(pos), _p(kv_len), 1 if pdl else 0, _stream()),
+         "groma_decode_head_argmax")
+    return logits
 
 
 def decode_reduce_rope_kv(ws: torch.Tensor, q_out: torch.Tensor, cache_k: torch.Tensor, cache_v: torch.Tensor, cos_t: torch.Tensor,

@@ -60,6 +60,18 @@ int32_t groma_gemm_bf16(const void* A, int64_t a_rows, int64_t lda, const void* 
                         const float* gamma, const void* residual, float* ws, int32_t split_k,
                         int32_t* tile_counters, int32_t conv_hp, int32_t conv_wp, int32_t block_n, void* stream);
 
+/* LLaMA attention input in ONE launch: x[B*T, K] @ w_qkv[3*H*D, K]^T (rows of w_qkv = [q heads | k heads | v heads]) with the
+ * rotate-half RoPE of q and k and the KV-cache append done in the GEMM epilogue -- the [B*T, 3*H*D] intermediate of
+ * groma_gemm_bf16 + groma_rope_kv never exists.  Replaces q_proj/k_proj/v_proj + apply_rotary_pos_emb + the cache torch.cat
+ * of $HF/models/llama/modeling_llama.py:199-246 (called from groma/model/groma.py:389-397).  Values are bit-identical to the
+ * two-launch form: the projection is rounded to bf16, rotated in fp32, rounded again.
+ * q_out [B*T, H*D] bf16; cache_k / cache_v [B, H, ctx_cap, D] bf16; cos_t / sin_t fp32 [max_pos, D/2]; token t of every
+ * sequence sits at position pos0 + t (pos0 + T <= ctx_cap).  D must be 128 and H even; block_n = 256 (one CTA per
+ * 128x256 tile) or 512 (cta_group::2 pair, 256x256). */
+int32_t groma_gemm_qkv_rope(const void* x, int64_t ldx, const void* w_qkv, int64_t ldw, int32_t B, int32_t T, int32_t H,
+                            int32_t D, int32_t K, void* q_out, void* cache_k, void* cache_v, const float* cos_t,
+                            const float* sin_t, int32_t pos0, int64_t ctx_cap, int32_t block_n, void* stream);
+
 /* out = epilogue(sum_s ws[s][M][N]) -- the deferred epilogue of a GROMA_GF_PARTIAL GEMM (same chain as above). */
 int32_t groma_splitk_reduce(const float* ws, int32_t splits, int32_t M, int32_t N, int32_t act, int32_t flags,
                             const float* bias, const float* gamma, const void* residual, void* out, int64_t ld_m,
@@ -199,6 +211,11 @@ int32_t groma_decode_advance(int32_t* pos, int32_t* kv_len, int32_t B, void* str
 int32_t groma_decode_reduce_norm(const float* ws, int32_t splits, int32_t B, int32_t N, void* x, const float* w, void* y,
                                  float eps, int32_t pdl, void* stream);
 int32_t groma_decode_reduce_swiglu(const float* ws, int32_t splits, int32_t B, int32_t N, void* out, int32_t pdl, void* stream);
+/* Tail of a decode step in one launch: logits[b, :] = sum_s ws[s][b][:] (fp32 [B, V], what lm_head returns,
+ * groma/model/groma.py:399-402), ids[b] = first maximal index (HF greedy_search's torch.argmax), then *pos += 1 and
+ * kv_len[b] += 1 for the next step.  Same values as groma_splitk_reduce + groma_argmax + groma_decode_advance. */
+int32_t groma_decode_head_argmax(const float* ws, int32_t splits, int32_t B, int32_t V, float* logits, int64_t* ids,
+                                 int32_t* pos, int32_t* kv_len, int32_t pdl, void* stream);
 int32_t groma_decode_reduce_rope_kv(const float* ws, int32_t splits, int32_t B, int32_t H, int32_t D, void* q_out, void* cache_k,
                                     void* cache_v, const float* cos_t, const float* sin_t, const int32_t* pos_ptr, int64_t cap,
                                     int32_t pdl, void* stream);

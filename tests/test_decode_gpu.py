@@ -106,6 +106,32 @@ def test_cluster_reduce_norm_matches_single_cta(G):
     assert ((y.float() - want).abs().max() / want.abs().max()).item() < 8e-3
 
 
+@pytest.mark.parametrize("B,V,S", [(16, 32114, 8), (3, 1000, 1), (5, 40, 11)])
+def test_head_tail_kernel_equals_reduce_argmax_advance(G, B, V, S):
+    """groma_decode_head_argmax == groma_splitk_reduce + groma_argmax + groma_decode_advance: logits bit for bit, first-index
+    tie-break across thread / CTA boundaries, position bookkeeping."""
+    ws = rnd(S, B, V, seed=21).cuda()
+    ws[:, 1] = 0.0                                   # one row where every column ties: index 0 wins
+    if V > 600:
+        ws[:, 0] = 0.0
+        ws[0, 0, [7, 513, V - 1]] = 50.0             # equal maxima in different threads and different cluster ranks
+        ws[0, 2, V - 1] = 60.0                       # maximum in the last (short) slice
+    want = torch.empty(B, V, device="cuda")
+    G.splitk_reduce(ws, want)
+    ids0 = G.argmax(want)
+    logits = torch.empty(B, V, device="cuda")
+    ids = torch.full((B,), -1, dtype=torch.int64, device="cuda")
+    pos = torch.tensor([41], dtype=torch.int32, device="cuda")
+    kvl = torch.arange(B, dtype=torch.int32, device="cuda") + 40
+    G.decode_head_argmax(ws, logits, ids, pos, kvl, pdl=False)
+    assert torch.equal(logits, want)
+    assert torch.equal(ids, ids0) and torch.equal(ids.cpu(), want.cpu().argmax(-1))
+    assert ids[1].item() == 0
+    if V > 600:
+        assert ids[0].item() == 7 and ids[2].item() == V - 1
+    assert pos.item() == 42 and torch.equal(kvl.cpu(), torch.arange(B, dtype=torch.int32) + 41)
+
+
 def test_fused_decode_step_is_bit_identical_to_unfused():
     """The fused reduce epilogues + programmatic dependent launch must not change a single bit of the decode logits."""
     from groma.model.groma import GromaConfig, GromaModel

@@ -254,6 +254,25 @@ def test_roi_align_oracle_edge_cases(G):
         assert torch.isfinite(got).all()
 
 
+def test_roi_align_bench_shape_and_channel_loop(G):
+    """The shared-tap kernel (fixed sampling grid) at the channel width of the bench (1024: one 16-byte vector per thread) and at
+    a width that makes the channel loop wrap (C/8 > 256 threads), against the oracle; RoIs include the reference's
+    cxcywh-fed-as-xyxy quirk (negative extents) and boxes that leave the map."""
+    for C, H, W, pool, sr in ((1024, 16, 16, 14, 2), (2304, 8, 8, 7, 2), (64, 32, 32, 14, 3)):
+        x = rnd(2, C, H, W, seed=90 + pool).bfloat16()
+        g = torch.Generator().manual_seed(91)
+        rois = torch.rand(24, 5, generator=g) * 448
+        rois[:, 0] = torch.randint(0, 2, (24,), generator=g).float()
+        rois[3:9, 3:] = rois[3:9, 1:3] * 0.4
+        rois[9:12, 1:] += 400.0
+        scale = H / 448.0
+        want = O.roi_align_ref(x.float(), rois, pool, scale, sr, True).permute(0, 2, 3, 1)
+        got = G.roi_align(dev(x.permute(0, 2, 3, 1).contiguous()), dev(rois), pool, scale, sr, True, pad=True).float().cpu()
+        assert got.shape == (24, pool + 2, pool + 2, C)
+        assert (got[:, 0] == 0).all() and (got[:, :, -1] == 0).all()
+        assert (got[:, 1:-1, 1:-1] - want).abs().max() <= 2e-2 * want.abs().max().clamp(min=1e-3)
+
+
 def test_nms_golden_and_oracle(G):
     # mmcv/tests/test_ops/test_nms.py:13-20 -> [1, 0, 3]
     b = torch.tensor([[6.0, 3.0, 8.0, 7.0], [3.0, 6.0, 9.0, 11.0], [3.0, 7.0, 10.0, 12.0], [1.0, 4.0, 13.0, 7.0]])
@@ -377,6 +396,29 @@ def test_vit_plumbing(G):
     f = ts[0][:, 1:].reshape(B, g, g, C)
     want = torch.cat([f[:, 0::2, 0::2], f[:, 1::2, 0::2], f[:, 0::2, 1::2], f[:, 1::2, 1::2]], -1).reshape(B, 4, 4 * C)
     assert torch.equal(s2d, want)
+
+
+@pytest.mark.parametrize("B,T,H,K,bn,pos0", [(2, 300, 4, 256, 256, 0), (3, 171, 2, 512, 256, 7), (2, 520, 6, 320, 512, 0)])
+def test_gemm_qkv_rope_equals_gemm_then_rope_kv(G, B, T, H, K, bn, pos0):
+    """groma_gemm_qkv_rope (RoPE + KV append in the GEMM epilogue) == groma_gemm_bf16 followed by groma_rope_kv, bit for bit:
+    q rows, the appended K/V rows, and nothing else in the cache touched (ragged last row tile, pos0 > 0, both tile shapes)."""
+    D, cap = 128, T + pos0 + 5
+    x = dev(rnd(B * T, K, seed=140).bfloat16())
+    w = dev((rnd(3 * H * D, K, seed=141) / math.sqrt(K)).bfloat16())
+    inv = 1.0 / (10000 ** (torch.arange(0, D, 2).float() / D))
+    fr = torch.outer(torch.arange(cap).float(), inv)
+    cos_t, sin_t = dev(fr.cos().contiguous()), dev(fr.sin().contiguous())
+    q0 = torch.empty(B * T, H * D, dtype=torch.bfloat16, device="cuda")
+    k0 = torch.full((B, H, cap, D), 3.0, dtype=torch.bfloat16, device="cuda"); v0 = k0.clone()
+    G.rope_kv(G.gemm(x, w), q0, k0, v0, cos_t, sin_t, B, T, H, D, pos0)
+    q1 = torch.empty_like(q0)
+    k1 = torch.full_like(k0, 3.0); v1 = k1.clone()
+    G.gemm_qkv_rope(x, w, q1, k1, v1, cos_t, sin_t, B, T, H, D, pos0, block_n=bn)
+    torch.cuda.synchronize()
+    for name, a, b in (("q", q0, q1), ("k", k0, k1), ("v", v0, v1)):
+        bad = (a != b)
+        assert not bad.any(), f"{name}: {int(bad.sum())} of {a.numel()} differ, max |d| {(a.float() - b.float()).abs().max().item():.3e}, first {bad.nonzero()[0].tolist()}"
+    assert (k1[:, :, :pos0] == 3.0).all() and (k1[:, :, pos0 + T:] == 3.0).all()
 
 
 def test_gather_scatter_rope_argmax(G):

@@ -18,6 +18,8 @@
 // TMEM: S_A [0,128) S_B [128,256) O_A [256,256+D) O_B [384,384+D) = all 512 columns, one CTA per SM.
 #include "ptx.cuh"
 #include "capi_common.h"
+#include "groma_b200.h"
+#include <cstdlib>
 
 namespace gb {
 
@@ -33,7 +35,15 @@ struct FaParams {
     int v_batch_rows, v_head_rows, v_head_cols;
     int q_pos0, causal;
     float scale_log2;
+    // raw views of the same tensors for the few keys past the last full 128-key tile (k_tail_max > 0: they are folded into the
+    // epilogue on CUDA cores instead of costing a whole masked tile pass); o_batch_rows = rows per batch of `o` (>= Sq)
+    const __nv_bfloat16 *q_ptr, *k_ptr, *v_ptr;
+    long long q_ld, k_ld, v_ld;
+    int k_tail_max, o_batch_rows;
+    int n_main;                             // query-tile pairs (grid.x)
 };
+__device__ __forceinline__ float2 bf16x2_to_f2(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+constexpr int FA_KTAIL = 8;   // at most this many trailing keys are handled in the epilogue (non-causal only)
 
 // UMMA smem descriptor, SWIZZLE_128B, explicit LBO/SBO (bytes)
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
@@ -90,7 +100,8 @@ template <int D>
 struct FaSmem {
     static constexpr int DBLK = D / 64;                 // 64-column (128-byte) blocks per row of Q/K/V
     static constexpr int TILE_BYTES = 128 * D * 2;      // one 128-row tile of Q, K or V
-    static constexpr int BYTES = 2 * TILE_BYTES + 2 * FA_STAGES * TILE_BYTES + 1024 + 256;
+    static constexpr int TAIL_BYTES = 2 * FA_KTAIL * D * 2;   // trailing K and V rows, staged for the epilogue
+    static constexpr int BYTES = 2 * TILE_BYTES + 2 * FA_STAGES * TILE_BYTES + 1024 + 256 + TAIL_BYTES;
 };
 
 template <int D>
@@ -111,14 +122,22 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa2q_kernel(const __g
     uint64_t* s_full = v_empty + FA_STAGES;             // [2 tiles]
     uint64_t* p_ready = s_full + 2;                     // [2]
     uint64_t* o_done = p_ready + 2;                     // [2]
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(o_done + 2);
+    uint64_t* tail_full = o_done + 2;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tail_full + 1);
+    __nv_bfloat16* tail_k = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(q_full) + 256);   // [FA_KTAIL][D]
+    __nv_bfloat16* tail_v = tail_k + FA_KTAIL * D;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // heavy (late, for causal) query blocks first: they have the most key tiles
-    const int qb = (int)gridDim.x - 1 - (int)blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int qb = p.n_main - 1 - (int)blockIdx.x;
     const int q0 = qb * 2 * FA_BM;
     int sk = p.Sk;
     if (p.kv_len) sk = min(sk, p.kv_len[b]);
+    // S = 1025 (ViT: 1024 patches + [CLS]) would spend a ninth, 127/128-masked tile pass on ONE key: up to k_tail_max trailing
+    // keys are instead added by each row's own thread in the epilogue (exact online-softmax merge, fp32 dot products)
+    const int k_tail = (!p.causal && (sk % FA_BN) <= p.k_tail_max) ? (sk % FA_BN) : 0;
+    sk -= k_tail;
     int n_x[2];                                         // key tiles each query tile has to visit
 #pragma unroll
     for (int X = 0; X < 2; ++X) {
@@ -137,6 +156,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa2q_kernel(const __g
             mbar_init(q_full, 1);
             for (int i = 0; i < FA_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
             for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_done[i], 1); }
+            mbar_init(tail_full, 1);
             fence_barrier_init();
         }
         __syncwarp();
@@ -242,6 +262,24 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa2q_kernel(const __g
         const uint32_t lane_sel = uint32_t(qw * 32) << 16;
         const uint32_t tmem_s = tmem_base + X * 128 + lane_sel, tmem_o = tmem_base + 256 + X * 128 + lane_sel;
         const int nt = n_x[X];
+        // one softmax warp stages the trailing key / value rows for the epilogue while the first S tile is still on its way (the
+        // global latency is paid here, once, under the TMA + first QK latency)
+        if (warp == 4) {
+        if (k_tail > 0) {
+            constexpr int CPR = D / 8, RPP = 32 / CPR;       // 16-byte chunks per row; rows copied per warp pass
+            const int ch = lane % CPR;
+            const __nv_bfloat16* ksrc = p.k_ptr + ((long long)b * p.k_batch_rows + (long long)h * p.k_head_rows + sk) * p.k_ld + (long long)h * p.k_head_cols + ch * 8;
+            const __nv_bfloat16* vsrc = p.v_ptr + ((long long)b * p.v_batch_rows + (long long)h * p.v_head_rows + sk) * p.v_ld + (long long)h * p.v_head_cols + ch * 8;
+            for (int t = lane / CPR; t < k_tail; t += RPP) {
+                const uint4 kk = *reinterpret_cast<const uint4*>(ksrc + (long long)t * p.k_ld);
+                const uint4 vv = *reinterpret_cast<const uint4*>(vsrc + (long long)t * p.v_ld);
+                *reinterpret_cast<uint4*>(tail_k + t * D + ch * 8) = kk;
+                *reinterpret_cast<uint4*>(tail_v + t * D + ch * 8) = vv;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tail_full);
+        }
+        }
         float m_used = 0.f, l_run = 0.f;
         const int q_limit = p.causal ? (p.q_pos0 + qi) : 0x7fffffff;   // last visible key for this row
         const int tile_first_limit = p.causal ? (p.q_pos0 + q0 + X * FA_BM) : 0x7fffffff;   // smallest q_limit of the tile
@@ -321,8 +359,62 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa2q_kernel(const __g
             mbar_wait(&o_done[X], (nt - 1) & 1);
             tc_fence_after();
         }
-        const float inv = (nt > 0 && l_run > 0.f) ? 1.f / l_run : 0.f;
-        __nv_bfloat16* dst = p.o + ((long long)b * p.Sq + qi) * p.o_ld + (long long)h * D;
+        // trailing keys (k_tail <= FA_KTAIL): x_t = scale * q_i . k_t in fp32, merged as one more online-softmax step
+        float f_old = 1.f, pt[FA_KTAIL];
+        const bool row_live = qi < p.Sq;
+        if (k_tail > 0) mbar_wait(tail_full, 0);          // completed long ago; acquires warp 2's staging stores
+        if (k_tail > 0 && row_live) {
+            uint32_t qr[D / 2];
+            if (n_max > 0) {
+                // the row sits in the Q tile the tensor core read: 128B-swizzled, 16-byte chunk c of row r at chunk c ^ (r & 7)
+                mbar_wait(q_full, 0);          // long complete; orders this thread's reads after the TMA writes
+                const uint8_t* qt = Qs + X * TILE + r * 128;
+#pragma unroll
+                for (int i = 0; i < D / 8; ++i)
+                    *reinterpret_cast<uint4*>(&qr[4 * i]) = *reinterpret_cast<const uint4*>(qt + (i >> 3) * (FA_BM * 128) + (((i & 7) ^ (r & 7)) << 4));
+            } else {
+                const __nv_bfloat16* qrow = p.q_ptr + ((long long)b * p.q_batch_rows + qi) * p.q_ld + (long long)h * p.q_head_cols;
+#pragma unroll
+                for (int i = 0; i < D / 8; ++i) *reinterpret_cast<uint4*>(&qr[4 * i]) = *reinterpret_cast<const uint4*>(qrow + 8 * i);
+            }
+            float xt[FA_KTAIL];
+            float m_fin = (nt > 0) ? m_used : -INFINITY;
+#pragma unroll
+            for (int t = 0; t < FA_KTAIL; ++t) {
+                xt[t] = -INFINITY;
+                if (t < k_tail) {
+                    const __nv_bfloat16* krow = tail_k + t * D;          // staged by warp 2; same address in every lane: broadcast
+                    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < D / 8; ++i) {
+                        const uint4 kv4 = *reinterpret_cast<const uint4*>(krow + 8 * i);
+                        const uint32_t kw[4] = {kv4.x, kv4.y, kv4.z, kv4.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float2 qf = bf16x2_to_f2(qr[4 * i + u]);
+                            const float2 kf = bf16x2_to_f2(kw[u]);
+                            a0 = fmaf(qf.x, kf.x, a0);
+                            a1 = fmaf(qf.y, kf.y, a1);
+                        }
+                    }
+                    xt[t] = (a0 + a1) * p.scale_log2;
+                    m_fin = fmaxf(m_fin, xt[t]);
+                }
+            }
+            f_old = (nt > 0) ? ex2_approx(m_used - m_fin) : 0.f;
+            l_run *= f_old;
+#pragma unroll
+            for (int t = 0; t < FA_KTAIL; ++t) {
+                pt[t] = (t < k_tail) ? ex2_approx(xt[t] - m_fin) : 0.f;
+                l_run += pt[t];
+                pt[t] = __bfloat162float(__float2bfloat16_rn(pt[t]));   // P enters the PV product in bf16, as in the tensor-core path
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < FA_KTAIL; ++t) pt[t] = 0.f;
+        }
+        const float inv = (l_run > 0.f) ? 1.f / l_run : 0.f;
+        __nv_bfloat16* dst = p.o + ((long long)b * p.o_batch_rows + qi) * p.o_ld + (long long)h * D;
 #pragma unroll
         for (int c = 0; c < D / 32; ++c) {
             uint32_t ov[32];
@@ -330,6 +422,26 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa2q_kernel(const __g
             else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) ov[i] = 0u;
+            }
+            if (k_tail > 0 && row_live) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * f_old);
+#pragma unroll
+                for (int t = 0; t < FA_KTAIL; ++t) {
+                    if (t >= k_tail) break;
+                    const __nv_bfloat16* vrow = tail_v + t * D + c * 32;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        const uint4 vv = *reinterpret_cast<const uint4*>(vrow + i);
+                        const uint32_t vw[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float2 vf = bf16x2_to_f2(vw[u]);
+                            ov[i + 2 * u] = __float_as_uint(fmaf(pt[t], vf.x, __uint_as_float(ov[i + 2 * u])));
+                            ov[i + 2 * u + 1] = __float_as_uint(fmaf(pt[t], vf.y, __uint_as_float(ov[i + 2 * u + 1])));
+                        }
+                    }
+                }
             }
             if (qi < p.Sq) {
 #pragma unroll
@@ -383,7 +495,7 @@ static int launch_fa(const FaParams& p, cudaStream_t st) {
         if (cudaFuncSetAttribute(attention_fa2q_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) return GROMA_ERR_CUDA;
         set = true;
     }
-    dim3 grid((p.Sq + 2 * FA_BM - 1) / (2 * FA_BM), p.H, p.B);
+    dim3 grid(p.n_main, p.H, p.B);
     attention_fa2q_kernel<D><<<grid, FA_THREADS, SMEM, st>>>(p);
     return GROMA_LAUNCH_CHECK();
 }
@@ -415,6 +527,15 @@ GROMA_API int32_t groma_attention_tc(const void* q, int64_t q_rows, int64_t q_co
     p.k_batch_rows = k_batch_rows; p.k_head_rows = k_head_rows; p.k_head_cols = k_head_cols;
     p.v_batch_rows = v_batch_rows; p.v_head_rows = v_head_rows; p.v_head_cols = v_head_cols;
     p.q_pos0 = q_pos0; p.causal = causal; p.scale_log2 = scale * 1.4426950408889634f;
+    p.q_ptr = reinterpret_cast<const __nv_bfloat16*>(q); p.k_ptr = reinterpret_cast<const __nv_bfloat16*>(k);
+    p.v_ptr = reinterpret_cast<const __nv_bfloat16*>(v);
+    p.q_ld = q_ld; p.k_ld = k_ld; p.v_ld = v_ld; p.o_batch_rows = Sq;
+    static const int tails = [] { const char* e = getenv("GROMA_FA_TAILS"); return e ? atoi(e) : 1; }();   // 0: A/B against the plain tiling
+    p.k_tail_max = tails ? FA_KTAIL : 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // (The one query row past the last full tile pair -- row 1024 of the ViT's 1025 -- still costs a fifth, single-tile CTA per
+    // head: moving it to CUDA-core CTAs of the same grid or to a second launch was measured and bought 2 us of 175, because a
+    // separate pass has to pull all of K and V again for one row; profiles/r02_fa_tails.md.)
+    p.n_main = (p.Sq + 2 * FA_BM - 1) / (2 * FA_BM);
     return D == 128 ? launch_fa<128>(p, st) : launch_fa<64>(p, st);
 }

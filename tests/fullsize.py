@@ -130,14 +130,16 @@ def run_fullsize_check(model, cfg, sd_f32: Dict[str, torch.Tensor], tok, n_text:
     new = gen[0, n_text:].cpu()
     wt, sl = want["new_tokens"][0], want["step_logits"][0]
     res["tokens_gpu"], res["tokens_oracle"] = new.tolist(), wt.tolist()
-    first_diff, margin_rel = None, None
+    first_diff, margin_rel, runner_up = None, None, None
     for t in range(n_new):
         if int(new[t]) != int(wt[t]):
-            top2 = sl[t].topk(2).values
-            first_diff, margin_rel = t, ((top2[0] - top2[1]) / sl[t].abs().max()).item()
+            top2 = sl[t].topk(2)
+            first_diff, margin_rel = t, ((top2.values[0] - top2.values[1]) / sl[t].abs().max()).item()
+            runner_up = int(new[t]) == int(top2.indices[1])
             break
     res["tokens_first_divergence"] = first_diff
     res["tokens_divergence_oracle_margin_rel"] = margin_rel
+    res["tokens_divergence_is_oracle_runner_up"] = runner_up
     res["tokens_equal"] = first_diff is None
     stepl = torch.stack([x.float().cpu()[0] for x in model._step_logits])
     n_cmp = n_new if first_diff is None else first_diff + 1
@@ -187,7 +189,12 @@ def run_fullsize_check(model, cfg, sd_f32: Dict[str, torch.Tensor], tok, n_text:
 # `*_max_abs` statistics are maxima over the 1200 box coordinates / 300 scores of decoder states that themselves sit 4-6e-2 from
 # their fp32 values: heavy-tailed (a query whose reference box lies near the inverse-sigmoid clamp amplifies its state's error),
 # so they get MAX_FACTOR; their `*_rms_abs` twins and every norm-relative stage distance get FLOOR_FACTOR.
-BARS = {"floor_factor": 1.5, "max_factor": 4.0, "eps": 2e-3, "token_margin_rel": 1e-2}
+# Greedy tokens: equal to the bf16 oracle's, or -- at the first difference -- the GPU must have picked the oracle's RUNNER-UP and the
+# oracle's own top-1 / top-2 margin (relative to max |logit| of that step, the unit of every `nrel` above) must lie inside
+# FLOOR_FACTOR x the measured bf16-vs-fp32 distance of the last-position logits: a near-tie that storage rounding alone can flip.
+# (A fixed 1e-2 stood here first; at Groma-7B the floor is 4e-2, and a 1.2e-2 tie flipped once the RoPE / RoIAlign kernels changed
+# their last-bit rounding, which is exactly the case the rule has to tell from a real divergence.)
+BARS = {"floor_factor": 1.5, "max_factor": 4.0, "eps": 2e-3}
 EXACT = ("topk_is_stable_argsort_of_own_scores", "nms_keep_exact_on_own_proposals", "selected_boxes_exact_on_own_proposals", "assembled_ids_exact")
 
 
@@ -209,6 +216,9 @@ def verdict(res: dict) -> list:
             bad.append(f"{k}: gpu-vs-bf16-oracle {got:.3e} > {fac} x floor {f:.3e} + {BARS['eps']}")
     if res["topk_overlap_with_oracle"] < 0.9:
         bad.append(f"two-stage top-k overlap with the oracle {res['topk_overlap_with_oracle']:.3f} < 0.9")
-    if not res["tokens_equal"] and res["tokens_divergence_oracle_margin_rel"] >= BARS["token_margin_rel"]:
-        bad.append(f"greedy tokens diverge at step {res['tokens_first_divergence']} with oracle margin {res['tokens_divergence_oracle_margin_rel']:.3e}")
+    if not res["tokens_equal"]:
+        lim = BARS["floor_factor"] * fl["logits_nrel_last_position"] + BARS["eps"]
+        if not res["tokens_divergence_is_oracle_runner_up"] or res["tokens_divergence_oracle_margin_rel"] > lim:
+            bad.append(f"greedy tokens diverge at step {res['tokens_first_divergence']}: oracle margin {res['tokens_divergence_oracle_margin_rel']:.3e} "
+                       f"(limit {lim:.3e}), gpu token is the oracle's runner-up: {res['tokens_divergence_is_oracle_runner_up']}")
     return bad

@@ -26,7 +26,11 @@ def ref_attn(q, k, v, causal, scale, q_pos0=0, kv_len=None):
 
 
 @pytest.mark.parametrize("B,H,S,D,causal", [(1, 1, 128, 128, False), (1, 1, 128, 64, False), (2, 3, 200, 128, True), (2, 2, 1025, 64, False),
-                                            (1, 2, 966, 128, True), (3, 2, 70, 64, True)])
+                                            (1, 2, 966, 128, True), (3, 2, 70, 64, True),
+                                            # key / query remainders that take the tail paths (<= 8 trailing keys merged in the epilogue,
+                                            # <= 16 trailing query rows on the mma.sync kernel) and their first non-tail neighbours
+                                            (2, 2, 1027, 128, False), (2, 3, 260, 64, False), (1, 2, 5, 64, False), (2, 1, 136, 128, False),
+                                            (1, 2, 137, 64, False), (1, 2, 528, 64, False), (1, 1, 529, 128, False), (2, 2, 1025, 64, True)])
 def test_attention_tc_cache_layout(B, H, S, D, causal):
     from groma_b200 import ops as G
     cap = S + 37
@@ -53,6 +57,11 @@ def test_attention_tc_qkv_layout_and_kvlen():
     kv_len = torch.tensor([300, 111], dtype=torch.int32)
     got = G.attention_tc(q, k, v, causal=False, scale=0.125, kv_len=kv_len.cuda()).float().cpu()
     xc = qkv.reshape(B, S, 3, H, D)
+    want = ref_attn(xc[:, :, 0], xc[:, :, 1].permute(0, 2, 1, 3), xc[:, :, 2].permute(0, 2, 1, 3), False, 0.125, 0, kv_len.long())
+    assert ((got - want).abs().max() / want.abs().max()).item() < 1e-2
+    # ragged non-causal lengths: one row ends 2 keys past a full tile (tail path), one does not
+    kv_len = torch.tensor([258, 300], dtype=torch.int32)
+    got = G.attention_tc(q, k, v, causal=False, scale=0.125, kv_len=kv_len.cuda()).float().cpu()
     want = ref_attn(xc[:, :, 0], xc[:, :, 1].permute(0, 2, 1, 3), xc[:, :, 2].permute(0, 2, 1, 3), False, 0.125, 0, kv_len.long())
     assert ((got - want).abs().max() / want.abs().max()).item() < 1e-2
     # causal + kv_len + right-padded rows (LLaMA prefill semantics): rows beyond kv_len still produce finite output

@@ -61,6 +61,10 @@ struct GemmParams {
     long long rope_cap;
 };
 
+#ifndef GROMA_EPI_V2
+#define GROMA_EPI_V2 1   // pipelined epilogue (A/B: tools/build_variants.sh epi1 -DGROMA_EPI_V2=0)
+#endif
+
 template <int BN, int CG = 1>
 struct GemmCfg {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
@@ -74,7 +78,8 @@ struct GemmCfg {
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
     static constexpr int EPW = gemm_epi_warps(BN);
     static constexpr int THREADS = gemm_threads(BN);
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPW * (32 * 80 + 32 * 8) /*epilogue staging*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPW * (32 * 80 + 32 * 8) /*epilogue staging*/ +
+                                      EPW * 1024 /*per-warp bias | gamma of the tile's columns*/;
 };
 
 // Grouped rasterisation: consecutive tiles walk GROUP_M m-blocks before advancing n, so the ~148 tiles in flight share
@@ -119,6 +124,7 @@ __global__ void __launch_bounds__(gemm_threads(BN), 1) gemm_bf16_tcgen05_kernel(
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    constexpr bool EPI2 = GROMA_EPI_V2 != 0;
 
     const int crank = (CG == 2) ? (int)cluster_ctarank() : 0;     // rank inside the CTA pair
     const int wid0 = blockIdx.x / CG, wstride = gridDim.x / CG;     // work is distributed over clusters
@@ -279,8 +285,10 @@ __global__ void __launch_bounds__(gemm_threads(BN), 1) gemm_bf16_tcgen05_kernel(
             m_blk = m_blk * CG + crank;
             const int it0 = split * iters_per_split;
             const bool has_work = it0 < total_iters;  // an empty split contributes zeros
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after();
+            if constexpr (!EPI2) {
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+            }
             const int row = m_blk * GEMM_BM + q * 32 + lane;
             bool row_ok = row < p.M;
             long long out_row = row;
@@ -300,7 +308,44 @@ __global__ void __launch_bounds__(gemm_threads(BN), 1) gemm_bf16_tcgen05_kernel(
             uint8_t* stg = stage_base + (warp - 2) * STG_WARP_BYTES;
             long long* stg_rows = reinterpret_cast<long long*>(stg + 32 * 80);
             if (staged) stg_rows[lane] = row_ok ? out_row : -1;
+            const uint32_t stg_s = smem_u32(stg);
+            bool released = false;
             int c_first = col_lo;
+            // EPI2: the bias / LayerScale values of this warp's columns are fetched ONCE per tile (one float4 of each per lane, while
+            // the tile's MMAs are still running) into a per-warp kilobyte of shared memory and read back as broadcast LDS.  As
+            // per-chunk global loads (8 + 8 LDG.128 per 32 columns) they missed the ~28 KB of L1 left beside 220 KB of shared memory
+            // -- the residual / output stream evicts them -- and every chunk paid a chain of L2 round trips.
+            const uint32_t bg_s = smem_u32(stage_base + Cfg::EPW * STG_WARP_BYTES + (warp - 2) * 1024);
+            const bool use_bg = EPI2 && !bias_m && !partial && (p.bias != nullptr || p.gamma != nullptr);
+            if (use_bg) {
+                __syncwarp();   // the previous tile's readers are done with the buffer
+                const int c = lane * 4;
+                if (c < BN / EPH) {
+                    const int n = n_blk * BN + col_lo + c;
+                    float b4[4] = {0.f, 0.f, 0.f, 0.f}, g4[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (p.bias != nullptr && n + u < p.N) b4[u] = __ldg(p.bias + n + u);
+                        if (p.gamma != nullptr && n + u < p.N) g4[u] = __ldg(p.gamma + n + u);
+                    }
+                    st_shared_v4(bg_s + c * 4, make_uint4(__float_as_uint(b4[0]), __float_as_uint(b4[1]), __float_as_uint(b4[2]), __float_as_uint(b4[3])));
+                    st_shared_v4(bg_s + 512 + c * 4, make_uint4(__float_as_uint(g4[0]), __float_as_uint(g4[1]), __float_as_uint(g4[2]), __float_as_uint(g4[3])));
+                }
+                __syncwarp();
+            }
+            if constexpr (EPI2) {
+                // While the tile's MMAs are still running: pull this lane's residual row segment (BN / EPH columns) towards L2, so
+                // the epilogue's residual loads are L2 hits instead of exposed DRAM round trips (the short-K ViT projections spent
+                // their epilogue in stall_long_sb on exactly these loads)
+                if (p.residual != nullptr && !partial && p.ld_n == 1 && row_ok) {
+                    const char* rp = reinterpret_cast<const char*>(p.residual + out_row * p.ld_m + (long long)n_blk * BN + col_lo);
+#pragma unroll
+                    for (int b = 0; b < (BN / EPH) * 2; b += 128)
+                        if (n_blk * BN + col_lo + (b >> 1) < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + b));
+                }
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+            }
             if constexpr (BN == 256 && Cfg::EPW == 8) {
                 if (p.flags & GF_ROPE_QKV) {
                     // This warp's 128 columns are exactly one head of q, k or v.  The projection is rounded to bf16 first (what the
@@ -362,15 +407,37 @@ __global__ void __launch_bounds__(gemm_threads(BN), 1) gemm_bf16_tcgen05_kernel(
                     }
                 }
             }
+            // EPI2: the residual row segment of a chunk is requested BEFORE its accumulators are read (the two latencies overlap),
+            // and the accumulator stage goes back to the MMA warp as soon as the last chunk sits in registers, not after it has
+            // been stored.  (Double-buffering the tcgen05.ld across chunks was tried as well: the 32 extra registers pushed
+            // loop invariants into local memory, and with ~28 KB of L1 those reloads are L2 round trips -- ncu showed every
+            // long-scoreboard stall of the epilogue on them; profiles/r02_gemm_epilogue_v2.md.)
+            const uint32_t tbase = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN);
+            const bool res_vec_ok = EPI2 && p.residual != nullptr && !partial && p.ld_n == 1 && (p.ld_m & 7) == 0;
 #pragma unroll 1
             for (int c0 = c_first; c0 < col_hi; c0 += CHUNK) {
                 uint32_t v[32];
-                const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + c0);
-                __syncwarp();  // tcgen05.ld is .sync.aligned (and orders the staging buffer reuse)
-                if (CHUNK == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
-                tmem_ld_wait();
                 const int n0 = n_blk * BN + c0;
                 const bool active = row_ok && n0 < p.N;
+                uint4 rpre[4];
+                const bool res_pre = res_vec_ok && active && CHUNK == 32 && n0 + CHUNK <= p.N;
+                if (res_pre) {
+                    const __nv_bfloat16* r = p.residual + out_row * p.ld_m + n0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) rpre[j] = __ldg(reinterpret_cast<const uint4*>(r) + j);
+                }
+                __syncwarp();  // tcgen05.ld is .sync.aligned (and orders the staging buffer reuse)
+                if (CHUNK == 32) tmem_ld32(tbase + c0, v); else tmem_ld16(tbase + c0, v);
+                tmem_ld_wait();
+                if constexpr (EPI2) {
+                    if (c0 + CHUNK >= col_hi && !(partial && p.tile_counters != nullptr)) {
+                        // every column of this warp's share is in registers: release the accumulator stage now
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) { if constexpr (CG == 2) mbar_arrive_cta(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]); }
+                        released = true;
+                    }
+                }
                 if (!staged && !active) continue;
                 if (!has_work) {
 #pragma unroll
@@ -410,6 +477,13 @@ __global__ void __launch_bounds__(gemm_threads(BN), 1) gemm_bf16_tcgen05_kernel(
                             const float bm = p.bias[row];
 #pragma unroll
                             for (int j = 0; j < CHUNK; ++j) f[j] += bm;
+                        } else if (use_bg) {
+#pragma unroll
+                            for (int j = 0; j < CHUNK; j += 4) {
+                                const uint4 b4 = ld_shared_v4(bg_s + (c0 - col_lo + j) * 4);
+                                f[j] += __uint_as_float(b4.x); f[j + 1] += __uint_as_float(b4.y);
+                                f[j + 2] += __uint_as_float(b4.z); f[j + 3] += __uint_as_float(b4.w);
+                            }
                         } else if (full) {
 #pragma unroll
                             for (int j = 0; j < CHUNK; j += 4) {
@@ -438,6 +512,13 @@ __global__ void __launch_bounds__(gemm_threads(BN), 1) gemm_bf16_tcgen05_kernel(
                                 const float gm = p.gamma[row];
 #pragma unroll
                                 for (int j = 0; j < CHUNK; ++j) f[j] *= gm;
+                            } else if (use_bg) {
+#pragma unroll
+                                for (int j = 0; j < CHUNK; j += 4) {
+                                    const uint4 g4 = ld_shared_v4(bg_s + 512 + (c0 - col_lo + j) * 4);
+                                    f[j] *= __uint_as_float(g4.x); f[j + 1] *= __uint_as_float(g4.y);
+                                    f[j + 2] *= __uint_as_float(g4.z); f[j + 3] *= __uint_as_float(g4.w);
+                                }
                             } else if (full) {
 #pragma unroll
                                 for (int j = 0; j < CHUNK; j += 4) {
@@ -454,7 +535,7 @@ __global__ void __launch_bounds__(gemm_threads(BN), 1) gemm_bf16_tcgen05_kernel(
                             if (p.ld_n == 1 && (p.ld_m & 7) == 0 && full) {
 #pragma unroll
                                 for (int j = 0; j < CHUNK; j += 8) {
-                                    const uint4 rv = *reinterpret_cast<const uint4*>(r + j);
+                                    const uint4 rv = res_pre ? rpre[(j >> 3) & 3] : *reinterpret_cast<const uint4*>(r + j);
                                     const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
                                     for (int t = 0; t < 4; ++t) {
@@ -468,6 +549,31 @@ __global__ void __launch_bounds__(gemm_threads(BN), 1) gemm_bf16_tcgen05_kernel(
                             }
                         }
                     }
+                }
+                if (EPI2 && staged && CHUNK == 32 && !swiglu && n0 + CHUNK <= p.N) {
+                    // 32 rows x 64 B through shared memory: 4 x STS.128 (own row), 4 x LDS.128 (4 lanes per row, 8 rows per
+                    // instruction), 4 x STG.128 writing 8 complete 64-byte row segments each -- no generic-address accesses and
+                    // no load -> branch -> load -> store chain per slot
+                    if (active) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            st_shared_v4(stg_s + lane * 80 + j * 16,
+                                         make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                                    pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7])));
+                    }
+                    __syncwarp();
+                    uint4 val[4];
+                    long long orow_k[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        orow_k[k] = ld_shared_b64(stg_s + 32 * 80 + (k * 8 + (lane >> 2)) * 8);
+                        val[k] = ld_shared_v4(stg_s + (k * 8 + (lane >> 2)) * 80 + (lane & 3) * 16);
+                    }
+                    __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out) + n0 + (lane & 3) * 8;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (orow_k[k] >= 0) *reinterpret_cast<uint4*>(ob + orow_k[k] * p.ld_m) = val[k];
+                    continue;
                 }
                 if (staged) {
                     const int pitch = out_cols * 2 + 16;  // +16 B: conflict-free 16-byte row writes
@@ -586,9 +692,11 @@ __global__ void __launch_bounds__(gemm_threads(BN), 1) gemm_bf16_tcgen05_kernel(
                 continue;
             }
             // release this accumulator stage back to the MMA warp (of the leader CTA)
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) { if constexpr (CG == 2) mbar_arrive_cta(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]); }
+            if (!released) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { if constexpr (CG == 2) mbar_arrive_cta(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]); }
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }

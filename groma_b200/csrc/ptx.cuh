@@ -128,6 +128,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Explicit shared-state-space accesses.  Pointers carved out of the dynamic shared-memory arena reach the compiler as generic
+// addresses and turn into LD.E / ST.E (generic path, long scoreboard); these stay LDS / STS.
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_shared_b64(uint32_t addr, long long v) {
+    asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ long long ld_shared_b64(uint32_t addr) {
+    long long v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 // Shared-memory matrix descriptor for a K-major bf16 tile stored as rows of 128 bytes (64 bf16) with the
 // 128-byte swizzle TMA produces (CU_TENSOR_MAP_SWIZZLE_128B).  Atom = 8 rows x 128 B, so the stride between
 // 8-row groups (SBO) is 1024 B; LBO is unused for a single swizzle atom along K.

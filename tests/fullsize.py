@@ -144,6 +144,17 @@ def run_fullsize_check(model, cfg, sd_f32: Dict[str, torch.Tensor], tok, n_text:
     stepl = torch.stack([x.float().cpu()[0] for x in model._step_logits])
     n_cmp = n_new if first_diff is None else first_diff + 1
     res["decode_step_logits_nrel"] = nrel(stepl[:n_cmp], sl[:n_cmp])
+    if first_diff is not None:
+        # Is the first difference a near-tie on BOTH sides?  gap = how far below its own best candidate each side rates the
+        # OTHER side's token, in units of max |logit| of that step (the unit of every `nrel`).  With random-init weights the
+        # logits are flat: several candidates can sit inside the storage-rounding noise of the top one, so "runner-up" is
+        # too narrow a description of a flip; what separates a flip from a real divergence is the size of these two gaps.
+        t, g_tok, o_tok = first_diff, int(new[first_diff]), int(wt[first_diff])
+        so, sg = sl[t].float(), stepl[t].float()
+        res["tokens_divergence_oracle_gap_rel"] = ((so[o_tok] - so[g_tok]) / so.abs().max()).item()
+        res["tokens_divergence_gpu_gap_rel"] = ((sg[g_tok] - sg[o_tok]) / sg.abs().max()).item()
+        res["tokens_divergence_oracle_rank_of_gpu_token"] = int((so > so[g_tok]).sum().item())
+        res["tokens_divergence_candidates_inside_limit"] = None   # filled by verdict() (needs the floor)
     # ---------------- the bf16-storage noise floor at this size: the SAME distances between the two oracles
     if fp32_floor:
         t0 = time.time()
@@ -189,11 +200,13 @@ def run_fullsize_check(model, cfg, sd_f32: Dict[str, torch.Tensor], tok, n_text:
 # `*_max_abs` statistics are maxima over the 1200 box coordinates / 300 scores of decoder states that themselves sit 4-6e-2 from
 # their fp32 values: heavy-tailed (a query whose reference box lies near the inverse-sigmoid clamp amplifies its state's error),
 # so they get MAX_FACTOR; their `*_rms_abs` twins and every norm-relative stage distance get FLOOR_FACTOR.
-# Greedy tokens: equal to the bf16 oracle's, or -- at the first difference -- the GPU must have picked the oracle's RUNNER-UP and the
-# oracle's own top-1 / top-2 margin (relative to max |logit| of that step, the unit of every `nrel` above) must lie inside
-# FLOOR_FACTOR x the measured bf16-vs-fp32 distance of the last-position logits: a near-tie that storage rounding alone can flip.
-# (A fixed 1e-2 stood here first; at Groma-7B the floor is 4e-2, and a 1.2e-2 tie flipped once the RoPE / RoIAlign kernels changed
-# their last-bit rounding, which is exactly the case the rule has to tell from a real divergence.)
+# Greedy tokens: equal to the bf16 oracle's, or -- at the first difference -- a near-tie on BOTH sides: the oracle's logit of the
+# GPU's token lies within LIM of the oracle's best, and the GPU's logit of the oracle's token within LIM of the GPU's best, LIM =
+# FLOOR_FACTOR x the measured bf16-vs-fp32 distance of the last-position logits (+ EPS), all relative to max |logit| of that step
+# (the unit of every `nrel` above): a tie that storage rounding alone can flip.  (A fixed 1e-2 top-1/top-2 margin stood here first,
+# then "the GPU's token must be the oracle's runner-up"; at Groma-7B the floor is 4e-2 and random-init logits are flat -- on the
+# 512-token bench prompt the flash-attention tail change moved a step-4 pick to a candidate the oracle ranks third, 1.2e-2 from its
+# best: rank is not the criterion, distance is.  Both gaps and the oracle's rank of the GPU token are reported.)
 BARS = {"floor_factor": 1.5, "max_factor": 4.0, "eps": 2e-3}
 EXACT = ("topk_is_stable_argsort_of_own_scores", "nms_keep_exact_on_own_proposals", "selected_boxes_exact_on_own_proposals", "assembled_ids_exact")
 
@@ -218,7 +231,10 @@ def verdict(res: dict) -> list:
         bad.append(f"two-stage top-k overlap with the oracle {res['topk_overlap_with_oracle']:.3f} < 0.9")
     if not res["tokens_equal"]:
         lim = BARS["floor_factor"] * fl["logits_nrel_last_position"] + BARS["eps"]
-        if not res["tokens_divergence_is_oracle_runner_up"] or res["tokens_divergence_oracle_margin_rel"] > lim:
-            bad.append(f"greedy tokens diverge at step {res['tokens_first_divergence']}: oracle margin {res['tokens_divergence_oracle_margin_rel']:.3e} "
-                       f"(limit {lim:.3e}), gpu token is the oracle's runner-up: {res['tokens_divergence_is_oracle_runner_up']}")
+        res["tokens_divergence_limit_rel"] = lim
+        og, gg = res["tokens_divergence_oracle_gap_rel"], res["tokens_divergence_gpu_gap_rel"]
+        if og > lim or gg > lim:
+            bad.append(f"greedy tokens diverge at step {res['tokens_first_divergence']} outside the noise floor: the oracle rates the GPU's "
+                       f"token {og:.3e} below its own (rank {res['tokens_divergence_oracle_rank_of_gpu_token']}), the GPU rates the "
+                       f"oracle's token {gg:.3e} below its own; limit {lim:.3e}")
     return bad

@@ -10,7 +10,10 @@ def timeit(fn, iters=10, warm=3):
         s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
         s.record(); fn(); e.record(); torch.cuda.synchronize(); ts.append(s.elapsed_time(e))
     ts.sort(); return ts[len(ts) // 2]
-for (M, N, K) in [(15456, 4096, 4096), (15456, 12288, 4096), (15456, 22016, 4096), (15456, 4096, 11008), (8192, 8192, 8192), (16400, 1024, 1024), (16400, 1024, 4096), (16400, 3072, 1024), (16400, 4096, 1024), (4800, 256, 256), (16384, 256, 1024), (1600, 4096, 1024)]:
+SHAPES = [(15456, 4096, 4096), (15456, 12288, 4096), (15456, 22016, 4096), (15456, 4096, 11008), (8192, 8192, 8192), (16400, 1024, 1024), (16400, 1024, 4096), (16400, 3072, 1024), (16400, 4096, 1024), (4800, 256, 256), (16384, 256, 1024), (1600, 4096, 1024)]
+if len(sys.argv) > 1 and sys.argv[1] == "vit":      # the short-K ViT projections + one LLaMA shape (epilogue A/B runs)
+    SHAPES = [(16400, 1024, 1024), (16400, 1024, 4096), (16400, 3072, 1024), (16400, 4096, 1024), (15456, 4096, 4096)]
+for (M, N, K) in SHAPES:
     a = torch.randn(M, K, device="cuda").bfloat16(); w = torch.randn(N, K, device="cuda").bfloat16()
     res = torch.randn(M, N, device="cuda").bfloat16(); gamma = torch.randn(N, device="cuda"); bias = torch.randn(N, device="cuda")
     out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)

@@ -81,7 +81,6 @@ reduce_residual_rmsnorm_cluster_kernel(const float* __restrict__ ws, int S, int 
                                        const float* __restrict__ w, __nv_bfloat16* __restrict__ y, float eps) {
     pdl_trigger();
     cluster_arrive_relaxed();   // DSMEM rule: peers must be running before their shared memory is written (waited on below)
-    pdl_wait();
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (int)cluster.block_rank();
@@ -92,12 +91,17 @@ reduce_residual_rmsnorm_cluster_kernel(const float* __restrict__ ws, int S, int 
     const int v = threadIdx.x;                   // one float4 per thread: slice <= 512
     const int col = crank * slice + v * 4;
     const bool act = v * 4 < slice;
+    // the norm weight is a parameter, not a product of the previous kernel: fetch it while that kernel is still running (it used
+    // to be loaded after the cluster barrier, one exposed L2 round trip on the critical path of each of the 64 calls per step)
+    float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (act) w4 = __ldg(reinterpret_cast<const float4*>(w + col));
+    pdl_wait();
     float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f;
     if (act) {
+        __nv_bfloat16* xp = x + (long long)b * N + col;
+        const uint2 xr = *reinterpret_cast<const uint2*>(xp);     // in flight together with the partials
         const float4 t = splitk_sum4(ws + (long long)b * N + col, (long long)B * N, S);
         h0 = t.x; h1 = t.y; h2 = t.z; h3 = t.w;
-        __nv_bfloat16* xp = x + (long long)b * N + col;
-        const uint2 xr = *reinterpret_cast<const uint2*>(xp);
         const float2 x01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xr.x));
         const float2 x23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xr.y));
         h0 = bf16_round(h0 + x01.x); h1 = bf16_round(h1 + x01.y); h2 = bf16_round(h2 + x23.x); h3 = bf16_round(h3 + x23.y);
@@ -115,7 +119,6 @@ reduce_residual_rmsnorm_cluster_kernel(const float* __restrict__ ws, int S, int 
     for (int r = 0; r < RN_CL; ++r) ss += part[r];
     const float rs = rsqrtf(ss / N + eps);
     if (act) {
-        const float4 w4 = *reinterpret_cast<const float4*>(w + col);
         *reinterpret_cast<uint2*>(y + (long long)b * N + col) =
             make_uint2(pack_bf16x2(w4.x * bf16_round(h0 * rs), w4.y * bf16_round(h1 * rs)),
                        pack_bf16x2(w4.z * bf16_round(h2 * rs), w4.w * bf16_round(h3 * rs)));

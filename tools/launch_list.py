@@ -37,7 +37,9 @@ md = ["# ncu launch list of ONE bench step, aggregated per kernel", "", f"comman
       "(per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes)", "",
       f"launches: {len(rows)}, sum of kernel time: {tot / 1000:.1f} ms", ""] + t
 # one decode step = the launches between two consecutive decode_advance kernels
-idx = [i for i, (n, _) in enumerate(rows) if n.startswith("decode_advance")]
+# (the last kernel of a step: reduce_head_argmax_cluster_kernel since the one-launch tail, decode_advance_kernel before it)
+idx = [i for i, (n, _) in enumerate(rows) if n.startswith("reduce_head_argmax_cluster")] or \
+      [i for i, (n, _) in enumerate(rows) if n.startswith("decode_advance")]
 if len(idx) >= 3:
     seg = rows[idx[-2] + 1: idx[-1] + 1]
     t2, tot2 = table(seg)

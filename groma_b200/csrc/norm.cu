@@ -1,6 +1,7 @@
 // Row-wise normalisation kernels (HBM-bound): RMSNorm, LayerNorm (+fused residual add), GroupNorm statistics and
 // GroupNorm+ReLU apply over NHWC maps.  bf16 in/out, fp32 math, 16-byte vector loads, one warp-shuffle tree per row.
 #include "ptx.cuh"
+#include "gn_common.cuh"
 #include "capi_common.h"
 
 namespace gb {
@@ -218,20 +219,7 @@ __global__ void gn_relu_apply_kernel(const __nv_bfloat16* __restrict__ x, const 
         const int g = (v * 8) / cpg;
         const float mean = stats[(b * G + g) * 2], rstd = stats[(b * G + g) * 2 + 1];
         const uint4 a = *reinterpret_cast<const uint4*>(x + i * 8);
-        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
-        float gg[8], bb[8];
-        *reinterpret_cast<float4*>(gg) = *reinterpret_cast<const float4*>(gamma + v * 8);
-        *reinterpret_cast<float4*>(gg + 4) = *reinterpret_cast<const float4*>(gamma + v * 8 + 4);
-        *reinterpret_cast<float4*>(bb) = *reinterpret_cast<const float4*>(beta + v * 8);
-        *reinterpret_cast<float4*>(bb + 4) = *reinterpret_cast<const float4*>(beta + v * 8 + 4);
-        uint32_t o[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const float2 f = __bfloat1622float2(a2[t]);
-            o[t] = pack_bf16x2(fmaxf((f.x - mean) * rstd * gg[2 * t] + bb[2 * t], 0.f),
-                               fmaxf((f.y - mean) * rstd * gg[2 * t + 1] + bb[2 * t + 1], 0.f));
-        }
-        *reinterpret_cast<uint4*>(y + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(y + i * 8) = gn_relu8(a, mean, rstd, gn_load_affine8(gamma, beta, v * 8));
     }
 }
 
@@ -274,11 +262,16 @@ GROMA_API int32_t groma_layernorm(const void* x, const void* residual, const flo
 }
 
 // GroupNorm(G) + ReLU over NHWC [B, P, C]; `part` is fp32 scratch of B*chunks*G*2, `stats` fp32 [B,G,2].
-GROMA_API int32_t groma_groupnorm_relu(const void* x, const float* gamma, const float* beta, void* y, float* part,
-                                       float* stats, int32_t B, int64_t P, int32_t C, int32_t G, float eps,
-                                       int32_t chunks, void* stream) {
-    if (!x || !gamma || !beta || !y || !part || !stats || B <= 0 || P <= 0 || C <= 0 || G <= 0) return GROMA_ERR_ARG;
-    if ((C & 7) || (C % G) || ((C / G) & 7) || chunks < 1) return GROMA_ERR_ALIGN;
+static int32_t gn_check(int32_t B, int64_t P, int32_t C, int32_t G) {
+    if (B <= 0 || P <= 0 || C <= 0 || G <= 0) return GROMA_ERR_ARG;
+    if ((C & 7) || (C % G) || ((C / G) & 7)) return GROMA_ERR_ALIGN;
+    return GROMA_OK;
+}
+GROMA_API int32_t groma_groupnorm_stats(const void* x, float* part, float* stats, int32_t B, int64_t P, int32_t C, int32_t G,
+                                        float eps, int32_t chunks, void* stream) {
+    if (!x || !part || !stats) return GROMA_ERR_ARG;
+    if (int32_t rc = gn_check(B, P, C, G)) return rc;
+    if (chunks < 1) return GROMA_ERR_ALIGN;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int nvec = C >> 3;
     int rows_par = 1024 / nvec;
@@ -290,10 +283,23 @@ GROMA_API int32_t groma_groupnorm_relu(const void* x, const float* gamma, const 
     gn_partial_kernel<<<dim3(chunks, B), threads, 2 * threads * sizeof(float), st>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), part, (int)P, C, G, ppc);
     gn_finalize_kernel<<<B, ((G + 31) / 32) * 32, 0, st>>>(part, stats, chunks, G, (float)((double)P * (C / G)), eps);
-    const long long total_vec = (long long)B * P * nvec;
+    return GROMA_LAUNCH_CHECK();
+}
+GROMA_API int32_t groma_groupnorm_apply_relu(const void* x, const float* stats, const float* gamma, const float* beta, void* y,
+                                             int32_t B, int64_t P, int32_t C, int32_t G, void* stream) {
+    if (!x || !stats || !gamma || !beta || !y) return GROMA_ERR_ARG;
+    if (int32_t rc = gn_check(B, P, C, G)) return rc;
+    const long long total_vec = (long long)B * P * (C >> 3);
     int blocks = (int)((total_vec + 255) / 256);
     if (blocks > 148 * 32) blocks = 148 * 32;
-    gn_relu_apply_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), stats, gamma, beta,
-                                                 reinterpret_cast<__nv_bfloat16*>(y), P, C, G, total_vec);
+    gn_relu_apply_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), stats, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), P, C, G, total_vec);
     return GROMA_LAUNCH_CHECK();
+}
+GROMA_API int32_t groma_groupnorm_relu(const void* x, const float* gamma, const float* beta, void* y, float* part,
+                                       float* stats, int32_t B, int64_t P, int32_t C, int32_t G, float eps,
+                                       int32_t chunks, void* stream) {
+    if (!gamma || !beta || !y) return GROMA_ERR_ARG;
+    if (int32_t rc = groma_groupnorm_stats(x, part, stats, B, P, C, G, eps, chunks, stream)) return rc;
+    return groma_groupnorm_apply_relu(x, stats, gamma, beta, y, B, P, C, G, stream);
 }

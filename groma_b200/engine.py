@@ -46,6 +46,7 @@ class GromaEngine:
         self.use_2cta = True           # cta_group::2 GEMM for the large prefill projections and 3x3 convs
         self.fused_head_tail = os.environ.get("GROMA_FUSED_HEAD_TAIL", "1") != "0"   # decode: head reduce + argmax + advance in one launch
         self.use_fused_rope = os.environ.get("GROMA_FUSED_ROPE", "1") != "0"   # RoPE + KV append in the qkv GEMM epilogue (prefill)
+        self.fuse_gn_apply = os.environ.get("GROMA_FUSE_GN", "1") != "0"       # GroupNorm + ReLU of a fusion round applied by the next round's shuffle
         # tcgen05 flash attention (attention_tcgen05.cu: two query tiles in ping-pong, P in tensor memory) for head dims 64 / 128
         # (DINOv2 and the LLaMA prefill); the mma.sync kernel stays for head dim 32 (Deformable-DETR self-attention) and the
         # miniature test shapes.  GROMA_TC_ATTENTION=0 switches back for A/B runs.
@@ -466,14 +467,28 @@ class GromaEngine:
             s = sizes[l]
             up = G.upsample_coords(hs[len(hs) - 3 + l], 1, g, s, s, self.in_ld, self.coord[s], self.coord[s])
             xs.append(G.gemm(up.reshape(-1, self.in_ld), w[f"inconv.{l}.w"], bias=w[f"inconv.{l}.b"]).reshape(B, s, s, C))
+        # Between fusion rounds the maps stay RAW conv outputs + GroupNorm statistics: the next round's shuffle applies norm + ReLU
+        # tap by tap (bit-identical to apply -> store -> shuffle, tests/test_ops_gpu.py), which drops one read + one write of every
+        # map per round; only the last round's maps are materialised for RoIAlign.  GROMA_FUSE_GN=0: the three-kernel form.
+        st = None                                       # per-level statistics of the maps in xs (None = xs is already activated)
         for k in range(cfg.fuse_rounds):
-            new = []
+            new, new_st = [], []
+            last = k == cfg.fuse_rounds - 1
             for l in range(3):
                 s = sizes[l]
-                xin = G.fuse_shuffle(xs[l], xs[min(l + 1, 2)], xs[max(l - 1, 0)])
+                t, d = min(l + 1, 2), max(l - 1, 0)
+                if st is None:
+                    xin = G.fuse_shuffle(xs[l], xs[t], xs[d])
+                else:
+                    xin = G.fuse_shuffle_gn(xs[l], xs[t], xs[d], st[l], st[t], st[d], w[f"fuse.{k - 1}.gn.w"], w[f"fuse.{k - 1}.gn.b"],
+                                            cfg.gn_groups)
                 y = G.conv3x3_flat(xin.reshape(-1, C), w[f"fuse.{k}.w"], B, s + 2, s + 2, block_n=512 if (self.use_2cta and C >= 512) else 0)
-                new.append(G.groupnorm_relu(y, w[f"fuse.{k}.gn.w"], w[f"fuse.{k}.gn.b"], cfg.gn_groups, 1e-5, B, out=y).reshape(B, s, s, C))
-            xs = new
+                if self.fuse_gn_apply and not last:
+                    new_st.append(G.groupnorm_stats(y, cfg.gn_groups, 1e-5, B))
+                    new.append(y.reshape(B, s, s, C))
+                else:
+                    new.append(G.groupnorm_relu(y, w[f"fuse.{k}.gn.w"], w[f"fuse.{k}.gn.b"], cfg.gn_groups, 1e-5, B, out=y).reshape(B, s, s, C))
+            xs, st = new, (new_st if (self.fuse_gn_apply and not last) else None)
         if self.keep_stages:
             self.stages["fused_maps"] = xs
         allb = torch.cat([b.float() for b in boxes]).to(self.dev)

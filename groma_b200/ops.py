@@ -316,6 +316,32 @@ def groupnorm_relu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, gro
     return out
 
 
+def groupnorm_stats(x: torch.Tensor, groups: int, eps: float, n_img: int, chunks: int = 0) -> torch.Tensor:
+    """x: [n_img * P, C] bf16 -> fp32 stats [n_img, groups, 2] (mean, rstd); the first half of groupnorm_relu."""
+    _bf16(x, "x")
+    C = x.shape[-1]
+    P = x.shape[0] // n_img
+    if chunks <= 0:
+        chunks = max(1, min(64, P // 256))
+    part = torch.empty((n_img * chunks * groups * 2,), dtype=torch.float32, device=x.device)
+    stats = torch.empty((n_img, groups, 2), dtype=torch.float32, device=x.device)
+    _chk(_L().groma_groupnorm_stats(_p(x), _p(part), _p(stats), n_img, P, C, groups, float(eps), chunks, _stream()), "groma_groupnorm_stats")
+    return stats
+
+
+def groupnorm_apply_relu(x: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, n_img: int,
+                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """relu((x - mean) * rstd * gamma + beta) with the statistics of groupnorm_stats; the second half of groupnorm_relu."""
+    _bf16(x, "x"); _f32(stats, "stats")
+    C = x.shape[-1]
+    P = x.shape[0] // n_img
+    if out is None:
+        out = torch.empty_like(x)
+    _chk(_L().groma_groupnorm_apply_relu(_p(x), _p(stats), _p(gamma), _p(beta), _p(out), n_img, P, C, groups, _stream()),
+         "groma_groupnorm_apply_relu")
+    return out
+
+
 # --------------------------------------------------------------------------------------------- detection ops
 def msda(value: torch.Tensor, proj: torch.Tensor, ref: torch.Tensor, level_hw: Sequence[Sequence[int]],
          n_heads: int, n_points: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -418,6 +444,23 @@ def fuse_shuffle(tar: torch.Tensor, top: torch.Tensor, down: torch.Tensor, out: 
     rc = _L().groma_fuse_shuffle(_p(tar), _p(top), _p(down), _p(out), B, C, Ht, Wt, top.shape[1], top.shape[2],
                                  down.shape[1], down.shape[2], _stream())
     _chk(rc, "groma_fuse_shuffle")
+    return out
+
+
+def fuse_shuffle_gn(tar: torch.Tensor, top: torch.Tensor, down: torch.Tensor, st_tar: torch.Tensor, st_top: torch.Tensor,
+                    st_down: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fuse_shuffle over RAW conv outputs: relu(GroupNorm) (per-level stats from groupnorm_stats, shared gamma / beta) is applied
+    to every tap; bit-identical to groupnorm_apply_relu on each map followed by fuse_shuffle."""
+    B, Ht, Wt, C = tar.shape
+    for t in (st_tar, st_top, st_down):
+        _f32(t, "stats")
+    if out is None:
+        out = torch.empty((B, Ht + 2, Wt + 2, C), dtype=torch.bfloat16, device=tar.device)
+    rc = _L().groma_fuse_shuffle_gn(_p(tar), _p(top), _p(down), _p(out), B, C, Ht, Wt, top.shape[1], top.shape[2],
+                                    down.shape[1], down.shape[2], _p(st_tar), _p(st_top), _p(st_down), _p(gamma), _p(beta),
+                                    groups, _stream())
+    _chk(rc, "groma_fuse_shuffle_gn")
     return out
 
 

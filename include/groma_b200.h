@@ -126,6 +126,13 @@ int32_t groma_layernorm(const void* x, const void* residual, const float* w, con
  * as used by groma/model/roi_align.py:133-143.  part: fp32 scratch [B*chunks*G*2]; stats: fp32 [B*G*2] (mean, rstd). */
 int32_t groma_groupnorm_relu(const void* x, const float* gamma, const float* beta, void* y, float* part, float* stats,
                              int32_t B, int64_t P, int32_t C, int32_t G, float eps, int32_t chunks, void* stream);
+/* The two halves of the call above: statistics only (stats [B,G,2] = mean, rstd) and apply + ReLU with given statistics.  The
+ * fusion rounds of MLVLFuseModule (groma/model/roi_align.py:118-126,180-193) keep the RAW conv outputs and let the next round's
+ * groma_fuse_shuffle_gn apply norm + act tap by tap; only the last round's maps are materialised with groma_groupnorm_apply_relu. */
+int32_t groma_groupnorm_stats(const void* x, float* part, float* stats, int32_t B, int64_t P, int32_t C, int32_t G, float eps,
+                              int32_t chunks, void* stream);
+int32_t groma_groupnorm_apply_relu(const void* x, const float* stats, const float* gamma, const float* beta, void* y, int32_t B,
+                                   int64_t P, int32_t C, int32_t G, void* stream);
 
 /* Multi-scale deformable attention forward; twin of mmcv `ms_deform_attn_forward`
  * (mmcv/ops/csrc/pytorch/pybind.cpp:162,765; kernel common/cuda/ms_deform_attn_cuda_kernel.cuh:203-256) with the
@@ -172,6 +179,13 @@ int32_t groma_upsample_coords(const void* tokens, int32_t skip, int32_t g, int32
                               int32_t Wo, int32_t ld, const float* xs, const float* ys, void* stream);
 int32_t groma_fuse_shuffle(const void* tar, const void* top, const void* down, void* out, int32_t B, int32_t C,
                            int32_t Ht, int32_t Wt, int32_t Htop, int32_t Wtop, int32_t Hdn, int32_t Wdn, void* stream);
+/* Same shuffle over the previous round's raw conv outputs: relu(GroupNorm_G) with per-level statistics and the round's shared
+ * gamma / beta (mmcv ConvModule norm + act, conv_module.py:196-206) is applied to every tap and rounded to bf16 first, so the
+ * result is bit-identical to groma_groupnorm_apply_relu on each map followed by groma_fuse_shuffle. */
+int32_t groma_fuse_shuffle_gn(const void* tar, const void* top, const void* down, void* out, int32_t B, int32_t C,
+                              int32_t Ht, int32_t Wt, int32_t Htop, int32_t Wtop, int32_t Hdn, int32_t Wdn,
+                              const float* stats_tar, const float* stats_top, const float* stats_down, const float* gamma,
+                              const float* beta, int32_t G, void* stream);
 
 /* DINOv2 embeddings (modeling_dinov2.py:57-149): im2col of 14x14 patches and CLS/pos-embed assembly. */
 int32_t groma_vit_patchify(const float* images, void* patches, int32_t B, int32_t S, int32_t ld, void* stream);

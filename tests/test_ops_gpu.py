@@ -202,6 +202,23 @@ def test_groupnorm_relu(G):
     assert rel_err(out, ref) < 5e-3
 
 
+def test_fuse_shuffle_gn_equals_apply_then_shuffle(G):
+    """groupnorm_stats + fuse_shuffle_gn over raw maps == groupnorm_relu on every map followed by fuse_shuffle, bit for bit
+    (the fusion rounds of the region encoder run the former; mmcv ConvModule norm + act, roi_align.py:118-126,150-178)."""
+    B, C, Gn = 2, 256, 16
+    gamma, beta = dev(rnd(C, seed=171)), dev(rnd(C, seed=172))
+    raw = [dev((rnd(B, s, s, C, seed=173 + i) * 3).bfloat16()) for i, s in enumerate((24, 12, 6))]
+    stats = [G.groupnorm_stats(m.reshape(-1, C), Gn, 1e-5, B) for m in raw]
+    act = [G.groupnorm_relu(m.reshape(-1, C).clone(), gamma, beta, Gn, 1e-5, B).reshape(m.shape) for m in raw]
+    for m, st, a in zip(raw, stats, act):     # the two halves of groupnorm_relu are the whole
+        assert torch.equal(G.groupnorm_apply_relu(m.reshape(-1, C), st, gamma, beta, Gn, B).reshape(m.shape), a)
+    for lvl in range(3):
+        top, dn = min(lvl + 1, 2), max(lvl - 1, 0)
+        want = G.fuse_shuffle(act[lvl], act[top], act[dn])
+        got = G.fuse_shuffle_gn(raw[lvl], raw[top], raw[dn], stats[lvl], stats[top], stats[dn], gamma, beta, Gn)
+        assert torch.equal(got, want), f"level {lvl}: {(got.float() - want.float()).abs().max().item()}"
+
+
 # ------------------------------------------------------------------------------------------------- detection ops
 def test_msda_matches_oracle(G):
     torch.manual_seed(3)

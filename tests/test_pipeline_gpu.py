@@ -116,6 +116,17 @@ def test_region_encoder(setup):
     e = nrel(reg_g, reg_o)
     print(f"region features nrel {e:.2e} rms {rmsrel(reg_g, reg_o):.2e}")
     assert e < 1.5e-2 and rmsrel(reg_g, reg_o) < 6e-3
+    # norm + ReLU folded into the next round's shuffle (default) == the three-kernel GroupNorm per round, bit for bit
+    assert m.engine.fuse_gn_apply
+    maps = [t.clone() for t in st["fused_maps"]]
+    m.engine.fuse_gn_apply = False
+    try:
+        reg_u = m.engine.region_encoder(hs_g, boxes)
+        for l in range(3):
+            assert torch.equal(m.engine.stages["fused_maps"][l], maps[l])
+        assert torch.equal(reg_u, reg_g)
+    finally:
+        m.engine.fuse_gn_apply = True
     empty = m.engine.region_encoder(hs_g, [torch.zeros(0, 4), torch.zeros(0, 4)])
     assert empty.shape == (0, setup["cfg"].llm_hidden)
 

@@ -41,6 +41,8 @@ struct FaParams {
     long long q_ld, k_ld, v_ld;
     int k_tail_max, o_batch_rows;
     int n_main;                             // query-tile pairs (grid.x)
+    int q_tail;                             // 1: query row n_main * 256 (the ViT's 1025th token) runs on the two idle warps of the
+                                            // producer warpgroup of CTA blockIdx.x == 0 of its head, against the K / V tiles in smem
 };
 __device__ __forceinline__ float2 bf16x2_to_f2(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
 constexpr int FA_KTAIL = 8;   // at most this many trailing keys are handled in the epilogue (non-causal only)
@@ -101,7 +103,8 @@ struct FaSmem {
     static constexpr int DBLK = D / 64;                 // 64-column (128-byte) blocks per row of Q/K/V
     static constexpr int TILE_BYTES = 128 * D * 2;      // one 128-row tile of Q, K or V
     static constexpr int TAIL_BYTES = 2 * FA_KTAIL * D * 2;   // trailing K and V rows, staged for the epilogue
-    static constexpr int BYTES = 2 * TILE_BYTES + 2 * FA_STAGES * TILE_BYTES + 1024 + 256 + TAIL_BYTES;
+    static constexpr int QT_BYTES = D * 2 + (D + 2) * 4 + 8;  // q_tail: the query row (bf16) + one warp's (m, l, acc[D]) for the merge
+    static constexpr int BYTES = 2 * TILE_BYTES + 2 * FA_STAGES * TILE_BYTES + 1024 + 256 + TAIL_BYTES + QT_BYTES;
 };
 
 template <int D>
@@ -126,6 +129,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa2q_kernel(const __g
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tail_full + 1);
     __nv_bfloat16* tail_k = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(q_full) + 256);   // [FA_KTAIL][D]
     __nv_bfloat16* tail_v = tail_k + FA_KTAIL * D;
+    __nv_bfloat16* qt_q = tail_v + FA_KTAIL * D;                                  // [D]   the tail query row
+    float* qt_merge = reinterpret_cast<float*>(qt_q + D);                          // [2 + D] warp 3's partial state
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // heavy (late, for causal) query blocks first: they have the most key tiles
@@ -147,6 +152,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa2q_kernel(const __g
         n_x[X] = (first < p.Sq) ? (k_end + FA_BN - 1) / FA_BN : 0;
     }
     const int n_max = max(n_x[0], n_x[1]);
+    // q_tail: this CTA also owns the one query row past the last full pair of tiles (non-causal, D = 64: the ViT)
+    const bool tail_cta = (D == 64) && p.q_tail > 0 && blockIdx.x == 0;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tma_q); tma_prefetch_desc(&p.tma_k); tma_prefetch_desc(&p.tma_v);
@@ -154,7 +161,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa2q_kernel(const __g
     if (warp == 1) {
         if (lane == 0) {
             mbar_init(q_full, 1);
-            for (int i = 0; i < FA_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+            // a stage is free once the MMAs that read it are complete AND, in a tail CTA, both tail warps are done with it
+            const uint32_t readers = 1 + (tail_cta ? 2 : 0);
+            for (int i = 0; i < FA_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], readers); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], readers); }
             for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_done[i], 1); }
             mbar_init(tail_full, 1);
             fence_barrier_init();
@@ -250,6 +259,116 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa2q_kernel(const __g
                 umma_commit(&v_empty[st]);                  // V_j free once both PV(j) are done
                 if (k_next_ready) umma_commit(&k_empty[stn]);   // K_{j+1} free once both QK(j+1) are done
             }
+        }
+    } else if (tail_cta) {
+        if constexpr (D == 64) {
+        // ---------------- warps 2, 3 of a tail CTA: query row qi = n_main * 256 on CUDA cores, out of the K / V tiles of the ring.
+        // Scores: lane = key (the 128-byte K row of a key is read as eight swizzled 16-byte chunks, the query row as broadcast
+        // chunks); PV: lane = dimension pair (P goes lane -> warp by shuffle, V as one 4-byte read per key).  Each warp takes 64
+        // keys of every tile; exponentials are referenced to a warp-uniform running maximum; the two warps' (m, l, acc) meet in
+        // shared memory; the keys past the last full tile (k_tail) are folded in last, as in the tensor-core rows' epilogue.
+        const int w = warp - 2;
+        const int qi = p.n_main * 2 * FA_BM;
+        const uint32_t ks_s = smem_u32(Ks), vs_s = smem_u32(Vs), qq_s = smem_u32(qt_q);
+        if (w == 0) {
+            const __nv_bfloat16* qrow = p.q_ptr + ((long long)b * p.q_batch_rows + qi) * p.q_ld + (long long)h * p.q_head_cols;
+            *reinterpret_cast<uint32_t*>(qt_q + 2 * lane) = *reinterpret_cast<const uint32_t*>(qrow + 2 * lane);
+        }
+        asm volatile("bar.sync 5, 64;" ::: "memory");
+        float m_run = -INFINITY, l_lane = 0.f, acc0 = 0.f, acc1 = 0.f;
+        for (int j = 0; j < n_max; ++j) {
+            const int st = j % FA_STAGES;
+            const uint32_t ph = (j / FA_STAGES) & 1;
+            mbar_wait(&k_full[st], ph);
+            float sc[2];
+#pragma unroll
+            for (int ps = 0; ps < 2; ++ps) {
+                const int r = w * 64 + ps * 32 + lane;               // key row inside the tile
+                const uint32_t krow = ks_s + st * TILE + r * 128;
+                float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint4 kv4 = ld_shared_v4(krow + ((c ^ (r & 7)) << 4));
+                    const uint4 qv4 = ld_shared_v4(qq_s + (c << 4));
+                    const uint32_t kw[4] = {kv4.x, kv4.y, kv4.z, kv4.w}, qw[4] = {qv4.x, qv4.y, qv4.z, qv4.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float2 kf = bf16x2_to_f2(kw[u]), qf = bf16x2_to_f2(qw[u]);
+                        d0 = fmaf(qf.x, kf.x, d0);
+                        d1 = fmaf(qf.y, kf.y, d1);
+                    }
+                }
+                sc[ps] = (j * FA_BN + r < sk) ? (d0 + d1) * p.scale_log2 : -INFINITY;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&k_empty[st]);
+            float tmax = fmaxf(sc[0], sc[1]);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, off));
+            const float m_new = fmaxf(m_run, tmax);                  // warp-uniform
+            mbar_wait(&v_full[st], ph);
+            if (m_new != -INFINITY) {
+                const float corr = ex2_approx(m_run - m_new);        // m_run = -inf -> 0
+                const float p0 = ex2_approx(sc[0] - m_new), p1 = ex2_approx(sc[1] - m_new);
+                l_lane = l_lane * corr + (p0 + p1);
+                acc0 *= corr; acc1 *= corr;
+                m_run = m_new;
+                const float pr0 = __bfloat162float(__float2bfloat16_rn(p0)), pr1 = __bfloat162float(__float2bfloat16_rn(p1));   // P enters PV in bf16
+                const uint32_t vcol = (uint32_t)(lane & 3) * 4;
+#pragma unroll 8
+                for (int kk = 0; kk < 64; ++kk) {
+                    const float pk = __shfl_sync(0xffffffffu, (kk < 32) ? pr0 : pr1, kk & 31);
+                    const int rr = w * 64 + kk;
+                    uint32_t vw;
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(vw) : "r"(vs_s + st * TILE + rr * 128 + ((((uint32_t)lane >> 2) ^ (rr & 7)) << 4) + vcol) : "memory");
+                    const float2 vf = bf16x2_to_f2(vw);
+                    acc0 = fmaf(pk, vf.x, acc0);
+                    acc1 = fmaf(pk, vf.y, acc1);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&v_empty[st]);
+        }
+        float l_w = l_lane;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) l_w += __shfl_xor_sync(0xffffffffu, l_w, off);
+        if (w == 1) {
+            if (lane == 0) { qt_merge[0] = m_run; qt_merge[1] = l_w; }
+            qt_merge[2 + 2 * lane] = acc0;
+            qt_merge[3 + 2 * lane] = acc1;
+        }
+        asm volatile("bar.sync 5, 64;" ::: "memory");
+        if (w == 0) {
+            const float m_o = qt_merge[0];
+            float m_fin = fmaxf(m_run, m_o);
+            float f_a = (m_fin == -INFINITY) ? 0.f : ex2_approx(m_run - m_fin), f_b = (m_fin == -INFINITY) ? 0.f : ex2_approx(m_o - m_fin);
+            float l_fin = l_w * f_a + qt_merge[1] * f_b;
+            acc0 = acc0 * f_a + qt_merge[2 + 2 * lane] * f_b;
+            acc1 = acc1 * f_a + qt_merge[3 + 2 * lane] * f_b;
+            if (k_tail > 0) {
+                mbar_wait(tail_full, 0);
+                const float2 qf = bf16x2_to_f2(*reinterpret_cast<const uint32_t*>(qt_q + 2 * lane));
+                for (int t = 0; t < k_tail; ++t) {
+                    const float2 kf = bf16x2_to_f2(*reinterpret_cast<const uint32_t*>(tail_k + t * D + 2 * lane));
+                    float x = fmaf(qf.x, kf.x, qf.y * kf.y);
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+                    x *= p.scale_log2;
+                    const float m2 = fmaxf(m_fin, x);
+                    const float f = (m_fin == -INFINITY) ? 0.f : ex2_approx(m_fin - m2);
+                    const float pt = ex2_approx(x - m2);
+                    l_fin = l_fin * f + pt;
+                    const float ptr_ = __bfloat162float(__float2bfloat16_rn(pt));
+                    const float2 vf = bf16x2_to_f2(*reinterpret_cast<const uint32_t*>(tail_v + t * D + 2 * lane));
+                    acc0 = fmaf(ptr_, vf.x, acc0 * f);
+                    acc1 = fmaf(ptr_, vf.y, acc1 * f);
+                    m_fin = m2;
+                }
+            }
+            const float inv = (l_fin > 0.f) ? 1.f / l_fin : 0.f;
+            __nv_bfloat16* dst = p.o + ((long long)b * p.o_batch_rows + qi) * p.o_ld + (long long)h * D;
+            *reinterpret_cast<uint32_t*>(dst + 2 * lane) = pack_bf16x2(acc0 * inv, acc1 * inv);
+        }
         }
     }
     } else {
@@ -458,7 +577,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa2q_kernel(const __g
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<512>(tmem_base);
+        // re-read from shared memory: keeping the address live across the 48-register warpgroup's branches made ptxas spill it
+        tmem_dealloc<512>(*reinterpret_cast<volatile uint32_t*>(tmem_holder));
     }
 }
 
@@ -530,12 +650,19 @@ GROMA_API int32_t groma_attention_tc(const void* q, int64_t q_rows, int64_t q_co
     p.q_ptr = reinterpret_cast<const __nv_bfloat16*>(q); p.k_ptr = reinterpret_cast<const __nv_bfloat16*>(k);
     p.v_ptr = reinterpret_cast<const __nv_bfloat16*>(v);
     p.q_ld = q_ld; p.k_ld = k_ld; p.v_ld = v_ld; p.o_batch_rows = Sq;
-    static const int tails = [] { const char* e = getenv("GROMA_FA_TAILS"); return e ? atoi(e) : 1; }();   // 0: A/B against the plain tiling
+    static const int tails = [] { const char* e = getenv("GROMA_FA_TAILS"); return e ? atoi(e) : 2; }();   // 0: plain tiling, 1: key tail only (A/B)
     p.k_tail_max = tails ? FA_KTAIL : 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    // (The one query row past the last full tile pair -- row 1024 of the ViT's 1025 -- still costs a fifth, single-tile CTA per
-    // head: moving it to CUDA-core CTAs of the same grid or to a second launch was measured and bought 2 us of 175, because a
-    // separate pass has to pull all of K and V again for one row; profiles/r02_fa_tails.md.)
+    // (Moving the one query row past the last full tile pair -- row 1024 of the ViT's 1025 -- to CUDA-core CTAs of the same grid or
+    // to a second launch was measured and bought 2 us of 175, because a separate pass has to pull all of K and V again for one
+    // row; profiles/r02_fa_tails.md.  q_tail below reads them from the shared-memory ring instead.)
     p.n_main = (p.Sq + 2 * FA_BM - 1) / (2 * FA_BM);
+    p.q_tail = 0;
+    // GROMA_FA_TAILS >= 2 (default): ONE query row past the last full pair of tiles (S = 1025) rides on the idle warps of the
+    // producer warpgroup instead of costing a fifth CTA per head -- 1024 CTAs are 6.92 waves of 148 SMs, 1280 were 8.65
+    if (tails >= 2 && D == 64 && !causal && p.Sq % (2 * FA_BM) == 1 && p.Sq > 2 * FA_BM) {
+        p.n_main = p.Sq / (2 * FA_BM);
+        p.q_tail = 1;
+    }
     return D == 128 ? launch_fa<128>(p, st) : launch_fa<64>(p, st);
 }

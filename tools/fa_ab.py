@@ -16,5 +16,5 @@ for _ in range(15):
     e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1) / 20)
 ts.sort()
 fl = 4.0 * B * H * S * S * D * (0.5 if causal else 1.0)
-print(f"[tails={os.environ.get('GROMA_FA_TAILS', '1')}] B={B} H={H} S={S} D={D} causal={causal}: min {ts[0]*1e3:.1f} us  median {ts[7]*1e3:.1f} us  "
+print(f"[tails={os.environ.get('GROMA_FA_TAILS', '2')}] B={B} H={H} S={S} D={D} causal={causal}: min {ts[0]*1e3:.1f} us  median {ts[7]*1e3:.1f} us  "
       f"-> {fl / ts[7] / 1e9:.0f} TFLOP/s (median)", flush=True)

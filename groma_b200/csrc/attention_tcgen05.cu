@@ -103,7 +103,8 @@ struct FaSmem {
     static constexpr int DBLK = D / 64;                 // 64-column (128-byte) blocks per row of Q/K/V
     static constexpr int TILE_BYTES = 128 * D * 2;      // one 128-row tile of Q, K or V
     static constexpr int TAIL_BYTES = 2 * FA_KTAIL * D * 2;   // trailing K and V rows, staged for the epilogue
-    static constexpr int QT_BYTES = D * 2 + (D + 2) * 4 + 8;  // q_tail: the query row (bf16) + one warp's (m, l, acc[D]) for the merge
+    // q_tail: the query row (bf16, then fp32) + one warp's (m, l, acc[D]) for the merge + each warp's 64 rounded probabilities
+    static constexpr int QT_BYTES = D * 2 + D * 4 + (D + 2) * 4 + 8 + 2 * 64 * 4;
     static constexpr int BYTES = 2 * TILE_BYTES + 2 * FA_STAGES * TILE_BYTES + 1024 + 256 + TAIL_BYTES + QT_BYTES;
 };
 
@@ -130,7 +131,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa2q_kernel(const __g
     __nv_bfloat16* tail_k = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(q_full) + 256);   // [FA_KTAIL][D]
     __nv_bfloat16* tail_v = tail_k + FA_KTAIL * D;
     __nv_bfloat16* qt_q = tail_v + FA_KTAIL * D;                                  // [D]   the tail query row
-    float* qt_merge = reinterpret_cast<float*>(qt_q + D);                          // [2 + D] warp 3's partial state
+    float* qt_qf = reinterpret_cast<float*>(qt_q + D);                             // [D]   the same row in fp32
+    float* qt_merge = qt_qf + D;                                                   // [2 + D] warp 3's partial state (+ 2 pad)
+    float* qt_p = qt_merge + D + 4;                                                // [2 warps][64] bf16-rounded probabilities of a tile
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // heavy (late, for causal) query blocks first: they have the most key tiles
@@ -269,10 +272,12 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa2q_kernel(const __g
         // shared memory; the keys past the last full tile (k_tail) are folded in last, as in the tensor-core rows' epilogue.
         const int w = warp - 2;
         const int qi = p.n_main * 2 * FA_BM;
-        const uint32_t ks_s = smem_u32(Ks), vs_s = smem_u32(Vs), qq_s = smem_u32(qt_q);
+        const uint32_t ks_s = smem_u32(Ks), vs_s = smem_u32(Vs), qf_s = smem_u32(qt_qf), pp_s = smem_u32(qt_p + w * 64);
         if (w == 0) {
             const __nv_bfloat16* qrow = p.q_ptr + ((long long)b * p.q_batch_rows + qi) * p.q_ld + (long long)h * p.q_head_cols;
-            *reinterpret_cast<uint32_t*>(qt_q + 2 * lane) = *reinterpret_cast<const uint32_t*>(qrow + 2 * lane);
+            const uint32_t qw = *reinterpret_cast<const uint32_t*>(qrow + 2 * lane);
+            *reinterpret_cast<uint32_t*>(qt_q + 2 * lane) = qw;
+            *reinterpret_cast<float2*>(qt_qf + 2 * lane) = bf16x2_to_f2(qw);     // converted once, not once per key
         }
         asm volatile("bar.sync 5, 64;" ::: "memory");
         float m_run = -INFINITY, l_lane = 0.f, acc0 = 0.f, acc1 = 0.f;
@@ -285,20 +290,18 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa2q_kernel(const __g
             for (int ps = 0; ps < 2; ++ps) {
                 const int r = w * 64 + ps * 32 + lane;               // key row inside the tile
                 const uint32_t krow = ks_s + st * TILE + r * 128;
-                float d0 = 0.f, d1 = 0.f;
-#pragma unroll
+                float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;       // four independent chains
+#pragma unroll 2                                                     // (48 registers per thread in this warpgroup: a full unroll spills)
                 for (int c = 0; c < 8; ++c) {
                     const uint4 kv4 = ld_shared_v4(krow + ((c ^ (r & 7)) << 4));
-                    const uint4 qv4 = ld_shared_v4(qq_s + (c << 4));
-                    const uint32_t kw[4] = {kv4.x, kv4.y, kv4.z, kv4.w}, qw[4] = {qv4.x, qv4.y, qv4.z, qv4.w};
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float2 kf = bf16x2_to_f2(kw[u]), qf = bf16x2_to_f2(qw[u]);
-                        d0 = fmaf(qf.x, kf.x, d0);
-                        d1 = fmaf(qf.y, kf.y, d1);
-                    }
+                    const uint4 qa = ld_shared_v4(qf_s + (c << 5)), qb = ld_shared_v4(qf_s + (c << 5) + 16);   // broadcast
+                    const float2 k0 = bf16x2_to_f2(kv4.x), k1 = bf16x2_to_f2(kv4.y), k2 = bf16x2_to_f2(kv4.z), k3 = bf16x2_to_f2(kv4.w);
+                    d0 = fmaf(__uint_as_float(qa.x), k0.x, d0); d1 = fmaf(__uint_as_float(qa.y), k0.y, d1);
+                    d2 = fmaf(__uint_as_float(qa.z), k1.x, d2); d3 = fmaf(__uint_as_float(qa.w), k1.y, d3);
+                    d0 = fmaf(__uint_as_float(qb.x), k2.x, d0); d1 = fmaf(__uint_as_float(qb.y), k2.y, d1);
+                    d2 = fmaf(__uint_as_float(qb.z), k3.x, d2); d3 = fmaf(__uint_as_float(qb.w), k3.y, d3);
                 }
-                sc[ps] = (j * FA_BN + r < sk) ? (d0 + d1) * p.scale_log2 : -INFINITY;
+                sc[ps] = (j * FA_BN + r < sk) ? ((d0 + d1) + (d2 + d3)) * p.scale_log2 : -INFINITY;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&k_empty[st]);
@@ -313,20 +316,28 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa2q_kernel(const __g
                 l_lane = l_lane * corr + (p0 + p1);
                 acc0 *= corr; acc1 *= corr;
                 m_run = m_new;
-                const float pr0 = __bfloat162float(__float2bfloat16_rn(p0)), pr1 = __bfloat162float(__float2bfloat16_rn(p1));   // P enters PV in bf16
-                const uint32_t vcol = (uint32_t)(lane & 3) * 4;
-#pragma unroll 8
-                for (int kk = 0; kk < 64; ++kk) {
-                    const float pk = __shfl_sync(0xffffffffu, (kk < 32) ? pr0 : pr1, kk & 31);
-                    const int rr = w * 64 + kk;
-                    uint32_t vw;
-                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(vw) : "r"(vs_s + st * TILE + rr * 128 + ((((uint32_t)lane >> 2) ^ (rr & 7)) << 4) + vcol) : "memory");
-                    const float2 vf = bf16x2_to_f2(vw);
-                    acc0 = fmaf(pk, vf.x, acc0);
-                    acc1 = fmaf(pk, vf.y, acc1);
+                // P enters PV in bf16, as on the tensor-core path; lane -> warp through shared memory (16 broadcast LDS.128, not 64 shuffles)
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(pp_s + lane * 4), "f"(__bfloat162float(__float2bfloat16_rn(p0))) : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(pp_s + 128 + lane * 4), "f"(__bfloat162float(__float2bfloat16_rn(p1))) : "memory");
+                __syncwarp();
+                const uint32_t vbase = vs_s + st * TILE + (w * 64) * 128 + (uint32_t)(lane & 3) * 4;
+                const uint32_t vch = (uint32_t)lane >> 2;
+#pragma unroll 4
+                for (int k4 = 0; k4 < 16; ++k4) {
+                    const uint4 p4 = ld_shared_v4(pp_s + (k4 << 4));
+                    const float pk[4] = {__uint_as_float(p4.x), __uint_as_float(p4.y), __uint_as_float(p4.z), __uint_as_float(p4.w)};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int rr = k4 * 4 + u;                    // (w * 64 + rr) & 7 == rr & 7
+                        uint32_t vw;
+                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(vw) : "r"(vbase + rr * 128 + ((vch ^ (rr & 7)) << 4)) : "memory");
+                        const float2 vf = bf16x2_to_f2(vw);
+                        acc0 = fmaf(pk[u], vf.x, acc0);
+                        acc1 = fmaf(pk[u], vf.y, acc1);
+                    }
                 }
             }
-            __syncwarp();
+            __syncwarp();                                            // (also: everyone is done with qt_p before the next tile rewrites it)
             if (lane == 0) mbar_arrive(&v_empty[st]);
         }
         float l_w = l_lane;

@@ -415,9 +415,12 @@ class GromaEngine:
 
     # ------------------------------------------------------------------------------------------ a10 region selection
     def select_regions(self, pc, px, sc, refer_boxes: Optional[Sequence[torch.Tensor]], ground_boxes: Optional[Sequence[torch.Tensor]],
-                       nms_thres: float, score_thres: float, max_num: int) -> List[torch.Tensor]:
+                       nms_thres: float, score_thres: float, max_num: int, overlap=None) -> List[torch.Tensor]:
         """groma.py:251-280.  NMS for the whole batch in one device kernel; the only host sync of the vision stage is the
-        read-back of keep indices.  torch.randperm stays on the global CPU RNG, one draw per image in image order (T6)."""
+        read-back of keep indices.  torch.randperm stays on the global CPU RNG, one draw per image in image order (T6).
+        `overlap`: a callable that enqueues GPU work which does not depend on the selection (the fusion convs of the region
+        encoder).  It is called after the read-back copies are queued and before the host waits for them, so the GPU keeps
+        running while the host reads the keep lists, draws the permutations and builds the RoI list."""
         cfg = self.cfg
         B, N = sc.shape
         Qn = cfg.num_queries
@@ -438,7 +441,23 @@ class GromaEngine:
                     o += n
                 counts[i] = o
         keep, num, amax = G.nms_batched(px, sc, nms_thres, score_thres, max_num, counts=counts.to(self.dev))
-        keep_h, num_h, amax_h, pc_h = keep.cpu(), num.cpu(), amax.cpu(), pc.cpu()   # single sync point
+        if overlap is None:
+            keep_h, num_h, amax_h, pc_h = keep.cpu(), num.cpu(), amax.cpu(), pc.cpu()   # single sync point
+        else:
+            # read-back into pinned buffers + an event: the host waits for these four copies only, not for what `overlap` queues
+            srcs = (keep, num, amax, pc)
+            key = tuple((tuple(t.shape), t.dtype) for t in srcs)
+            if getattr(self, "_sel_pinned_key", None) != key:
+                with torch.inference_mode(False):      # persistent buffers: ordinary tensors even under a caller's inference_mode()
+                    self._sel_pinned = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in srcs]
+                self._sel_pinned_key = key
+            for dst, src in zip(self._sel_pinned, srcs):
+                dst.copy_(src, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            overlap()
+            ev.synchronize()
+            keep_h, num_h, amax_h, pc_h = (t.clone() for t in self._sel_pinned)
         self._stage("nms_keep", keep_h); self._stage("nms_num", num_h)
         from .dist import replayed_randperms
         perms = replayed_randperms([int(n) for n in num_h])   # == [torch.randperm(n)] in a single process
@@ -457,7 +476,14 @@ class GromaEngine:
     # ------------------------------------------------------------------------------------------ a12/a13 region encoder
     def region_encoder(self, hs: List[torch.Tensor], boxes: Sequence[torch.Tensor]) -> torch.Tensor:
         """groma/model/roi_align.py:215-228 (upsample), :97-193 (MLVLFuseModule), :274-327 (MlvlRoIExtractor).
-        boxes: per-image [R_i,4] cxcywh (host or device).  Returns region features [sum R, llm_hidden] bf16."""
+        boxes: per-image [R_i,4] cxcywh (host or device).  Returns region features [sum R, llm_hidden] bf16.
+        = region_tokens(region_maps(hs), boxes); GromaModel calls the halves separately so that the maps (which do not depend on
+        the selected boxes) are already being computed while the host reads the NMS result back."""
+        return self.region_tokens(self.region_maps(hs), boxes)
+
+    def region_maps(self, hs: List[torch.Tensor]) -> List[torch.Tensor]:
+        """The box-independent part: upsample + coord channels + 1x1 input convs (roi_align.py:215-228,118-126) and the fusion
+        rounds of MLVLFuseModule (:180-193).  Returns the three fused NHWC maps [B, s, s, C], s = 4g, 2g, g."""
         cfg, w = self.cfg, self.w
         g, C = cfg.grid, cfg.vit_hidden
         B = hs[0].shape[0]
@@ -491,6 +517,13 @@ class GromaEngine:
             xs, st = new, (new_st if (self.fuse_gn_apply and not last) else None)
         if self.keep_stages:
             self.stages["fused_maps"] = xs
+        return xs
+
+    def region_tokens(self, xs: List[torch.Tensor], boxes: Sequence[torch.Tensor]) -> torch.Tensor:
+        """MlvlRoIExtractor.forward (roi_align.py:274-327) on the fused maps of region_maps: RoIAlign x3 -> pconvs -> sum -> ReLU ->
+        flatten_linear + box position MLP -> updims."""
+        cfg, w = self.cfg, self.w
+        C = cfg.vit_hidden
         allb = torch.cat([b.float() for b in boxes]).to(self.dev)
         K = allb.shape[0]
         if K == 0:

@@ -455,12 +455,19 @@ class GromaEngine:
                 dst.copy_(src, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
-            overlap()
+            # multi-rank: replayed_randperms all-gathers the keep counts on this stream right after the read-back; queue the
+            # overlapped work behind those (tiny) collectives, not in front of them
+            import torch.distributed as _dist
+            overlap_late = _dist.is_available() and _dist.is_initialized() and _dist.get_world_size() > 1
+            if not overlap_late:
+                overlap()
             ev.synchronize()
             keep_h, num_h, amax_h, pc_h = (t.clone() for t in self._sel_pinned)
         self._stage("nms_keep", keep_h); self._stage("nms_num", num_h)
         from .dist import replayed_randperms
         perms = replayed_randperms([int(n) for n in num_h])   # == [torch.randperm(n)] in a single process
+        if overlap is not None and overlap_late:
+            overlap()
         selected = []
         for i in range(B):
             n = int(num_h[i])

@@ -72,3 +72,21 @@ def test_attention_tc_qkv_layout_and_kvlen():
     want = ref_attn(q, kc[:, :, :S], vc[:, :, :S], True, 0.088, 0, kv_len.long())
     assert torch.isfinite(got).all()
     assert ((got - want).abs().max() / want.abs().max()).item() < 1e-2
+
+
+def test_attention_tc_query_tail_row_with_ragged_kv():
+    """Sq = 2 * 256 + 1, D = 64, non-causal: the last query row runs on the producer warpgroup's idle warps (q_tail) out of the
+    shared-memory K / V ring.  Ragged kv_len exercises its masking (a partly valid last tile), the trailing-key merge (kv_len 2
+    past a full tile) and a row with fewer keys than one tile."""
+    from groma_b200 import ops as G
+    B, S, H, D = 4, 513, 2, 64
+    q = rnd(B, S, H, D, seed=21).bfloat16(); kc = rnd(B, H, S, D, seed=22).bfloat16(); vc = rnd(B, H, S, D, seed=23).bfloat16()
+    for lens in ([513, 130, 258, 7], [513, 513, 512, 385]):
+        kv_len = torch.tensor(lens, dtype=torch.int32)
+        got = G.attention_tc(q.cuda(), kc.cuda(), vc.cuda(), causal=False, scale=0.125, kv_len=kv_len.cuda(), sk=S).float().cpu()
+        want = ref_attn(q, kc, vc, False, 0.125, 0, kv_len.long())
+        assert torch.isfinite(got).all()
+        err_all = ((got - want).abs().max() / want.abs().max()).item()
+        err_tail = ((got[:, -1] - want[:, -1]).abs().max() / want.abs().max()).item()
+        print(f"kv_len {lens}: norm-rel err {err_all:.2e}, tail row {err_tail:.2e}")
+        assert err_all < 1e-2 and err_tail < 1e-2
